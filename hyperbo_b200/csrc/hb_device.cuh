@@ -1,0 +1,326 @@
+// hyperbo_b200 device building blocks (sm_100a).
+//
+// Data layout in HBM (DESIGN.md "Data layout"): every task's symmetric /
+// triangular matrix (K~ -> L, and L^{-1}) is stored as PACKED LOWER-TRIANGULAR
+// 64x64 TILES; tile (i,j), i >= j, lives at tile slot i(i+1)/2 + j and is one
+// contiguous 64*64*sizeof(Real) block so that it moves with ONE 1-D TMA bulk
+// copy (cp.async.bulk -> SASS UBLKCP).  Inside a tile, elements are grouped in
+// 8x4 micro-blocks (8 rows x 4 cols, row-major inside, 32 scalars contiguous);
+// micro-blocks are ordered [row_block(8)][col_block(16)].  One micro-block is
+// exactly one warp-wide MMA operand fragment (lane = 4*(row&7) + (col&3)), so
+// every fragment load is a single conflict-free, fully coalesced shared-memory
+// request, for both the K-major and the MN-major operand role.  The same
+// ordering is the tcgen05 SWIZZLE_NONE K-major canonical layout for 4-byte
+// types (8 rows x 16 B core matrices), which is what the fp32 path needs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr int TB = 64;                 // tile edge
+constexpr int TILE_ELEMS = TB * TB;    // 4096 scalars per tile
+constexpr int NTHREADS = 256;          // 8 warps per CTA
+constexpr int MAX_DIM = 32;
+
+struct TaskDesc {
+  int n;               // true number of points
+  int nblk;            // ceil(n / 64)
+  long long xoff;      // first row of this task in X / y
+  long long voff;      // offset into 64-padded per-task vectors (z, alpha)
+  long long tile_off;  // first tile slot of this task in the packed buffers
+  long long chol_off;  // element offset of this task's (n,n) row-major factor
+};
+
+__host__ __device__ __forceinline__ int tri_idx(int i, int j) {
+  return i * (i + 1) / 2 + j;
+}
+// offset of element (r, c) inside a 64x64 tile
+__host__ __device__ __forceinline__ int elem_off(int r, int c) {
+  return ((((r >> 3) << 4) + (c >> 2)) << 5) + ((r & 7) << 2) + (c & 3);
+}
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (UBLKCP.S.G)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem,
+                                         uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// 1-D TMA bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem,
+                                         uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::
+                   "l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// order generic-proxy smem accesses before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// fp64 tensor-core MMA (DMMA.8x8x4): C(8x8) += A(8x4,row) * B(4x8,col)
+// lane = 4*g + t :  a = A[g][t],  b = B[t][g],  c = {C[g][2t], C[g][2t+1]}
+__device__ __forceinline__ void mma_884(double (&c)[2], double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, "
+      "{%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------- fragment loads ----
+enum Major { KMAJOR = 0, MNMAJOR = 1 };
+
+// Operand stored as tile[idx][k] (idx = output row/col, k = contraction):
+// the 8(idx) x 4(k) fragment of idx-block `blk8`, k-block `kb` is micro-block
+// (blk8, kb): 32 contiguous scalars, lane-ordered.
+template <typename Real>
+__device__ __forceinline__ Real frag_kmajor(const Real* tile, int blk8, int kb,
+                                            int lane) {
+  return tile[(((blk8 << 4) + kb) << 5) + lane];
+}
+// Operand stored as tile[k][idx]: element (k = 4kb + t, idx = 8 blk8 + g).
+template <typename Real>
+__device__ __forceinline__ Real frag_mnmajor(const Real* tile, int blk8, int kb,
+                                             int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  return tile[((((kb >> 1) << 4) + (blk8 << 1) + (g >> 2)) << 5) +
+              ((((kb & 1) << 2) + t) << 2) + (g & 3)];
+}
+
+// Warp roles inside the 256-thread CTA for one 64x64 output tile:
+//   wk = warp >> 2 : split-K half (k-blocks [8wk, 8wk+8))
+//   wq = warp & 3  : 32x32 quadrant, wm = wq >> 1 (rows), wn = wq & 1 (cols)
+// acc[fm][fn][e]: rows 32wm + 8fm + g, cols 32wn + 8fn + 2t + e.
+struct WarpPos {
+  int warp, lane, wk, wm, wn, g, t;
+  __device__ __forceinline__ WarpPos() {
+    warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    wk = warp >> 2;
+    wm = (warp >> 1) & 1;
+    wn = warp & 1;
+    g = lane >> 2;
+    t = lane & 3;
+  }
+};
+
+template <int AM, int BM>
+__device__ __forceinline__ void tile_mma(double (&acc)[4][4][2],
+                                         const double* __restrict__ As,
+                                         const double* __restrict__ Bs,
+                                         const WarpPos& w, int kb_lo = 0,
+                                         int kb_hi = 16) {
+  // the two split-K warp groups share the non-zero k-block range
+  // [kb_lo, kb_hi) evenly (callers pass the non-zero range of triangular
+  // operands so that structural zeros are never multiplied)
+  const int kmid = kb_lo + ((kb_hi - kb_lo + 1) >> 1);
+  const int k0 = w.wk ? kmid : kb_lo, k1 = w.wk ? kb_hi : kmid;
+#pragma unroll 2
+  for (int kb = k0; kb < k1; ++kb) {
+    double a[4], b[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      a[f] = (AM == KMAJOR) ? frag_kmajor(As, 4 * w.wm + f, kb, w.lane)
+                            : frag_mnmajor(As, 4 * w.wm + f, kb, w.lane);
+      b[f] = (BM == KMAJOR) ? frag_kmajor(Bs, 4 * w.wn + f, kb, w.lane)
+                            : frag_mnmajor(Bs, 4 * w.wn + f, kb, w.lane);
+    }
+#pragma unroll
+    for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) mma_884(acc[fm][fn], a[fm], b[fn]);
+  }
+}
+
+__device__ __forceinline__ void acc_zero(double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+
+// After the k loop the two split-K halves hold partial sums of the same
+// quadrant.  Exchange through shared memory so that warp (wk, wq) ends up
+// owning the fully reduced rows 32wm + 16wk + 8fi + g (fi = 0,1) of its
+// quadrant:  own[fi][fn][e].  `xc` is a TILE_ELEMS scratch buffer.
+__device__ __forceinline__ void splitk_exchange(double (&acc)[4][4][2],
+                                                double (&own)[2][4][2],
+                                                double* xc, const WarpPos& w) {
+  const int wq = w.warp & 3;
+  // send the half this warp does NOT keep to slot (wq, dest wk = 1 - wk);
+  // static register indices only (a runtime index would spill acc to local)
+  {
+    double2* dst = reinterpret_cast<double2*>(xc) +
+                   (((wq * 2 + (1 - w.wk)) * 8) << 5) + w.lane;
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) {
+        const double2 v = w.wk ? make_double2(acc[fi][fn][0], acc[fi][fn][1])
+                               : make_double2(acc[2 + fi][fn][0],
+                                              acc[2 + fi][fn][1]);
+        dst[(fi * 4 + fn) << 5] = v;
+      }
+  }
+  __syncthreads();
+  {
+    const double2* src = reinterpret_cast<const double2*>(xc) +
+                         (((wq * 2 + w.wk) * 8) << 5) + w.lane;
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) {
+        const double2 v = src[(fi * 4 + fn) << 5];
+        own[fi][fn][0] = (w.wk ? acc[2 + fi][fn][0] : acc[fi][fn][0]) + v.x;
+        own[fi][fn][1] = (w.wk ? acc[2 + fi][fn][1] : acc[fi][fn][1]) + v.y;
+      }
+  }
+  fence_async_smem();
+  __syncthreads();
+}
+
+// row / col (inside the 64x64 tile) of own[fi][fn][e]
+__device__ __forceinline__ int own_row(const WarpPos& w, int fi) {
+  return 32 * w.wm + 16 * w.wk + 8 * fi + w.g;
+}
+__device__ __forceinline__ int own_col(const WarpPos& w, int fn, int e) {
+  return 32 * w.wn + 8 * fn + 2 * w.t + e;
+}
+
+// write own[][][] into a shared-memory tile buffer in tile layout
+__device__ __forceinline__ void own_to_tile(const double (&own)[2][4][2],
+                                            double* tile, const WarpPos& w) {
+#pragma unroll
+  for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn) {
+      const int r = own_row(w, fi), c = own_col(w, fn, 0);
+      *reinterpret_cast<double2*>(tile + elem_off(r, c)) =
+          make_double2(own[fi][fn][0], own[fi][fn][1]);
+    }
+}
+
+// ----------------------------------------------------- streamed tile GEMM ---
+struct TilePair {
+  const double* a;  // global tile for operand A (nullptr: use fixed smem A)
+  const double* b;  // global tile for operand B (nullptr: fixed smem B;
+                    //  == a: reuse the A tile)
+  int kb_lo, kb_hi; // non-zero k-block range of this product
+};
+
+struct Pipe {
+  uint64_t* full;  // [2] mbarriers
+  double* stA;     // [2][TILE_ELEMS]
+  double* stB;     // [2][TILE_ELEMS]
+  uint32_t it;     // tiles consumed so far by this CTA (uniform)
+};
+
+// acc += sum_k A_k * B_k, tiles streamed from global memory with a 2-stage TMA
+// bulk-copy pipeline (tile k+1 in flight while tile k feeds the tensor pipe).
+// Caller guarantees a __syncthreads() since the last generic access to the
+// stage buffers.  `hook(k, As, Bs)` runs on every tile while it is resident.
+template <int AM, int BM, class Fn, class Hook>
+__device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K,
+                                            Fn fn, Pipe& p,
+                                            const double* Afixed,
+                                            const double* Bfixed, Hook hook,
+                                            const WarpPos& w) {
+  constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(double);
+  auto issue = [&](int k, uint32_t itk) {
+    const TilePair tp = fn(k);
+    const int s = itk & 1;
+    const bool lb = tp.b != nullptr && tp.b != tp.a;
+    const uint32_t bytes = (tp.a ? TILE_BYTES : 0u) + (lb ? TILE_BYTES : 0u);
+    mbar_expect_tx(&p.full[s], bytes);
+    if (tp.a) bulk_g2s(p.stA + s * TILE_ELEMS, tp.a, TILE_BYTES, &p.full[s]);
+    if (lb) bulk_g2s(p.stB + s * TILE_ELEMS, tp.b, TILE_BYTES, &p.full[s]);
+  };
+  if (threadIdx.x == 0) {
+    if (K > 0) issue(0, p.it);
+    if (K > 1) issue(1, p.it + 1);
+  }
+  for (int k = 0; k < K; ++k) {
+    const int s = p.it & 1;
+    mbar_wait(&p.full[s], (p.it >> 1) & 1);
+    const TilePair tp = fn(k);
+    const double* As = tp.a ? p.stA + s * TILE_ELEMS : Afixed;
+    const double* Bs = (tp.b == nullptr) ? Bfixed
+                       : (tp.b == tp.a)  ? As
+                                         : p.stB + s * TILE_ELEMS;
+    tile_mma<AM, BM>(acc, As, Bs, w, tp.kb_lo, tp.kb_hi);
+    hook(k, As, Bs);
+    __syncthreads();
+    if (threadIdx.x == 0 && k + 2 < K) issue(k + 2, p.it + 2);
+    ++p.it;
+  }
+}
+
+struct NoHook {
+  __device__ __forceinline__ void operator()(int, const double*,
+                                             const double*) const {}
+};
+
+// ------------------------------------------------------------ reductions ---
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// deterministic block sum; `red` has >= 8 doubles; result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < NTHREADS / 32; ++i) s += red[i];
+  return s;
+}
+
+}  // namespace hb

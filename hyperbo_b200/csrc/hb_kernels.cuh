@@ -1,0 +1,1011 @@
+// hyperbo_b200 kernels: batched GP NLL + gradient on packed 64x64 tiles.
+//
+// Reference arithmetic restated (paths under /root/reference/hyperbo/):
+//   kernel build        gp_utils/kernel.py:63-123, basics/linalg.py:36-69
+//   Cholesky + solves   basics/linalg.py:29-33,72-110,139-171
+//   NLL value           gp_utils/objectives.py:144-156,178-195
+//   gradient            closed form of jax.value_and_grad at gp_utils/gp.py:134
+//   Adam                optax.adam as used at gp_utils/gp.py:124,143-144
+//
+// Algorithm per task (all tasks of a call advance together, one launch per
+// block column): left-looking blocked Cholesky on 64x64 tiles whose trailing
+// tile products run on the fp64 tensor pipe (DMMA), with the kernel matrix
+// evaluated on the fly (K~ never hits memory), the triangular inverse
+// M = L^{-1} built row by row in the SAME launches, then K~^{-1} = M'M formed
+// tile by tile and contracted against dK/dtheta in the epilogue (K~^{-1} never
+// hits memory either).
+#pragma once
+#include "hb_device.cuh"
+
+namespace hb {
+
+// theta buffer layout (doubles), written by k_prep
+constexpr int TH_CONST = 0, TH_SV = 1, TH_NV = 2, TH_LS = 3;
+constexpr int TH_INVLS = TH_LS + MAX_DIM;            // 35
+constexpr int TH_CHAIN = TH_INVLS + MAX_DIM;         // 67 (3 + MAX_DIM entries)
+constexpr int TH_SIZE = 128;
+constexpr double JITTER = 1e-6;    // basics/linalg.py:42
+constexpr double EPS_WARP = 1e-10; // gp_utils/utils.py:28,73
+
+struct Params {
+  const TaskDesc* tasks;
+  int T, d;
+  int kernel_id, mean_id;
+  int with_trtri;
+  const double* X;
+  const double* y;
+  const double* theta;
+  double* Lt;       // packed tiles of L
+  double* Mt;       // packed tiles of M = L^{-1} (diag tiles: inv of diag blocks)
+  double* z;        // L^{-1} r, 64-padded per task
+  double* alpha;    // K~^{-1} r, 64-padded per task
+  double* logdet;   // per (task, block): sum_k log L_kk of that diagonal block
+  double* asum;     // per (task, block): sum of alpha over the block
+  double* nll_task; // per task
+  double* gpart;    // per tile slot: [2 + MAX_DIM] gradient partials
+  double* gtask;    // per task: [2 + MAX_DIM]
+  int* info;        // per task: 0 or failing column + 1
+  unsigned* bad;    // per task scratch: min failing column + 1, ~0u if none
+};
+
+constexpr int GP_STRIDE = 2 + MAX_DIM;  // [sv, nv, ls...]
+
+// shared-memory map (bytes) of the tile kernels
+constexpr int SM_BARS = 0;
+constexpr int SM_RED = 64;                              // 16 doubles
+constexpr int SM_STA = 192;
+constexpr int SM_STB = SM_STA + 2 * TILE_ELEMS * 8;
+constexpr int SM_CS = SM_STB + 2 * TILE_ELEMS * 8;
+constexpr int SM_PS = SM_CS + TILE_ELEMS * 8;
+constexpr int SM_VEC = SM_PS + TILE_ELEMS * 8;          // 2 x 64 doubles
+constexpr int SM_X = SM_VEC + 2 * 64 * 8;
+__host__ __device__ inline int xstride(int d) { return d | 1; }
+__host__ inline size_t step_smem_bytes(int d) {
+  return SM_X + 2 * 64 * xstride(d) * 8;
+}
+// the lauum/grad and predict kernels do not need Cs/Ps
+constexpr int SL_VEC = SM_CS;                           // 2 x 64 doubles
+constexpr int SL_RED2 = SL_VEC + 2 * 64 * 8;            // 8 x GP_STRIDE doubles
+constexpr int SL_X = SL_RED2 + 8 * GP_STRIDE * 8;
+__host__ inline size_t lauum_smem_bytes(int d) {
+  return SL_X + 2 * 64 * xstride(d) * 8;
+}
+
+// ------------------------------------------------------------------ prep ---
+__device__ __forceinline__ double softplus(double x) {
+  return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x));
+}
+__device__ __forceinline__ double sigmoid(double x) {
+  return 1.0 / (1.0 + exp(-x));
+}
+
+// raw -> theta (params_utils.retrieve_params + utils.DEFAULT_WARP_FUNC), the
+// chain-rule factors d theta / d raw, and per-call state reset.
+__global__ void k_prep(const double* __restrict__ raw, uint32_t warp_mask,
+                       int d, int mean_id, double* __restrict__ theta,
+                       unsigned* bad, int T) {
+  const int p = threadIdx.x;
+  if (p < 3 + d) {
+    const double r = raw[p];
+    const bool wp = (warp_mask >> p) & 1u;
+    double v = wp ? softplus(r) + EPS_WARP : r;
+    double ch = wp ? sigmoid(r) : 1.0;
+    if (p == 0 && mean_id == 0) { v = 0.0; ch = 0.0; }
+    theta[TH_CHAIN + p] = ch;
+    if (p < 3) theta[p] = v;
+    else {
+      theta[TH_LS + (p - 3)] = v;
+      theta[TH_INVLS + (p - 3)] = 1.0 / v;
+    }
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) bad[t] = 0xffffffffu;
+}
+
+// ------------------------------------------------------- kernel functions ---
+// k and the pair weight W with dK/dl_k = W * Delta_k^2 / l_k^3
+template <int KID>
+__device__ __forceinline__ void kern_eval(double r2, double sv, double& k,
+                                          double& wgt) {
+  if (KID == 0) {  // squared_exponential, kernel.py:63-81
+    k = sv * exp(-0.5 * r2);
+    wgt = k;
+  } else if (KID == 1) {  // matern32, kernel.py:84-102
+    const double r = sqrt(3.0 * r2);
+    const double e = exp(-r);
+    k = sv * (1.0 + r) * e;
+    wgt = 3.0 * sv * e;
+  } else {  // matern52, kernel.py:105-123
+    const double r = sqrt(5.0 * r2);
+    const double e = exp(-r);
+    k = sv * (1.0 + r + r * r * (1.0 / 3.0)) * e;
+    wgt = (5.0 / 3.0) * sv * (1.0 + r) * e;
+  }
+}
+
+// load the 64 x d block `blk` of a task's inputs, scaled by 1/lengthscale,
+// rows beyond n zero-filled.  xs[r * DP + k].
+__device__ __forceinline__ void load_xblock(double* xs, const double* X,
+                                            long long row0, int nvalid, int d,
+                                            int DP, const double* theta) {
+  for (int e = threadIdx.x; e < 64 * d; e += NTHREADS) {
+    const int r = e / d, k = e - r * d;
+    xs[r * DP + k] =
+        (r < nvalid) ? X[(row0 + r) * d + k] * theta[TH_INVLS + k] : 0.0;
+  }
+}
+
+// own[fi][fn][e] <- K~ tile (bi, bj) evaluated from the scaled input blocks.
+// Padding rows/cols (>= n) make K~ the identity there.  If `sub`, computes
+// K~ - own instead.  wout (optional) receives the pair weights W.
+template <int KID, bool SUB>
+__device__ __forceinline__ void ktile_eval(double (&own)[2][4][2],
+                                           const double* xi, const double* xj,
+                                           int d, int DP, int row0, int col0,
+                                           int n, double sv, double diag_add,
+                                           const WarpPos& w) {
+  double r2[2][4][2];
+#pragma unroll
+  for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn) r2[fi][fn][0] = r2[fi][fn][1] = 0.0;
+  for (int k = 0; k < d; ++k) {
+    double xr[2], xc[4][2];
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi) xr[fi] = xi[own_row(w, fi) * DP + k];
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) xc[fn][e] = xj[own_col(w, fn, e) * DP + k];
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double df = xr[fi] - xc[fn][e];
+          r2[fi][fn][e] = fma(df, df, r2[fi][fn][e]);
+        }
+  }
+#pragma unroll
+  for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gr = row0 + own_row(w, fi), gc = col0 + own_col(w, fn, e);
+        double k, wg;
+        kern_eval<KID>(r2[fi][fn][e], sv, k, wg);
+        if (gr == gc) k += diag_add;
+        if (gr >= n || gc >= n) k = (gr == gc) ? 1.0 : 0.0;
+        own[fi][fn][e] = SUB ? k - own[fi][fn][e] : k;
+      }
+}
+
+// ------------------------------------------------------------- step kernel --
+// One launch per block column j (j = -1 .. nblk_max-1).  State on entry:
+// L(:, <j), L(j,j), M(j,j) = L(j,j)^{-1}, z_{<=j} and rows < j of M are final.
+// Roles (blockIdx.x) of task blockIdx.y:
+//   role 0 .. np-1 : panel tile i = j+1+role:  L(i,j) = (K(i,j) - sum_{k<j}
+//                    L(i,k) L(j,k)') M(j,j)'            [tensor-pipe GEMMs]
+//        role 0 then also factors the NEXT diagonal block (look-ahead):
+//                    A = K~(i,i) - sum_{k<=j} L(i,k) L(i,k)',  L(i,i) = chol(A),
+//                    M(i,i) = L(i,i)^{-1},  z_i = M(i,i) (r_i - sum L(i,k) z_k)
+//   then j roles   : row j of M:  M(j,c) = -M(j,j) sum_{k=c}^{j-1} L(j,k) M(k,c)
+template <int KID>
+__global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TaskDesc td = P.tasks[blockIdx.y];
+  const int nblk = td.nblk;
+  if (nblk == 0) return;
+  const int np = (j < 0) ? 1 : max(0, nblk - 1 - j);
+  const int nt = (P.with_trtri && j >= 1 && j < nblk) ? j : 0;
+  const int role = blockIdx.x;
+  if (role >= np + nt) return;
+
+  const WarpPos w;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+  double* red = reinterpret_cast<double*>(smem + SM_RED);
+  double* stA = reinterpret_cast<double*>(smem + SM_STA);
+  double* stB = reinterpret_cast<double*>(smem + SM_STB);
+  double* Cs = reinterpret_cast<double*>(smem + SM_CS);
+  double* Ps = reinterpret_cast<double*>(smem + SM_PS);
+  double* vec = reinterpret_cast<double*>(smem + SM_VEC);
+  const int DP = xstride(P.d);
+  double* xi = reinterpret_cast<double*>(smem + SM_X);
+  double* xj = xi + 64 * DP;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  Pipe pipe{bars, stA, stB, 0u};
+  constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(double);
+
+  const double* Lt = P.Lt + td.tile_off * TILE_ELEMS;
+  double* Ltw = P.Lt + td.tile_off * TILE_ELEMS;
+  const double* Mt = P.Mt + td.tile_off * TILE_ELEMS;
+  double* Mtw = P.Mt + td.tile_off * TILE_ELEMS;
+  const double sv = P.theta[TH_SV];
+  const double nv = P.theta[TH_NV];
+  double acc[4][4][2];
+  double own[2][4][2];
+
+  // ------------------------------------------------------------ trtri role
+  if (role >= np) {
+    const int c = role - np;
+    acc_zero(acc);
+    stream_gemm<KMAJOR, MNMAJOR>(
+        acc, j - c,
+        [&](int kk) {
+          const int k = c + kk;
+          // M(c,c) is lower triangular: rows k'' >= cols n; as B[k''][n] all
+          // k'' contribute for some n -> full range (kept simple)
+          return TilePair{Lt + (size_t)tri_idx(j, k) * TILE_ELEMS,
+                          Mt + (size_t)tri_idx(k, c) * TILE_ELEMS, 0, 16};
+        },
+        pipe, nullptr, nullptr, NoHook(), w);
+    splitk_exchange(acc, own, stA, w);
+    own_to_tile(own, Cs, w);
+    __syncthreads();
+    acc_zero(acc);
+    stream_gemm<KMAJOR, MNMAJOR>(
+        acc, 1,
+        [&](int) {
+          return TilePair{Mt + (size_t)tri_idx(j, j) * TILE_ELEMS, nullptr, 0,
+                          16};
+        },
+        pipe, nullptr, Cs, NoHook(), w);
+    splitk_exchange(acc, own, stA, w);
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) {
+        own[fi][fn][0] = -own[fi][fn][0];
+        own[fi][fn][1] = -own[fi][fn][1];
+      }
+    own_to_tile(own, Ps, w);
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(Mtw + (size_t)tri_idx(j, c) * TILE_ELEMS, Ps, TILE_BYTES);
+      bulk_commit();
+      bulk_wait_all();
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------ panel role
+  const int i = (j < 0) ? 0 : j + 1 + role;
+  const long long rowi = td.xoff + 64LL * i;
+  load_xblock(xi, P.X, rowi, min(64, td.n - 64 * i), P.d, DP, P.theta);
+  if (j >= 0) {
+    load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
+                P.theta);
+    acc_zero(acc);
+    stream_gemm<KMAJOR, KMAJOR>(
+        acc, j,
+        [&](int k) {
+          return TilePair{Lt + (size_t)tri_idx(i, k) * TILE_ELEMS,
+                          Lt + (size_t)tri_idx(j, k) * TILE_ELEMS, 0, 16};
+        },
+        pipe, nullptr, nullptr, NoHook(), w);
+    splitk_exchange(acc, own, stA, w);  // also orders the xi/xj loads
+    ktile_eval<KID, true>(own, xi, xj, P.d, DP, 64 * i, 64 * j, td.n, sv, 0.0,
+                          w);
+    own_to_tile(own, Cs, w);
+    __syncthreads();
+    acc_zero(acc);
+    stream_gemm<KMAJOR, KMAJOR>(
+        acc, 1,
+        [&](int) {
+          return TilePair{nullptr, Mt + (size_t)tri_idx(j, j) * TILE_ELEMS, 0,
+                          16};
+        },
+        pipe, Cs, nullptr, NoHook(), w);
+    splitk_exchange(acc, own, stA, w);
+    own_to_tile(own, Ps, w);
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(Ltw + (size_t)tri_idx(i, j) * TILE_ELEMS, Ps, TILE_BYTES);
+      bulk_commit();
+    }
+    if (role != 0) {
+      if (threadIdx.x == 0) bulk_wait_all();
+      return;
+    }
+  }
+
+  // ------------------------------------- look-ahead: factor diagonal block i
+  // rhs partial: lane (g,t) of warp w accumulates sum_k L(i,k)[8w+g][.] z_k[.]
+  double rhs_part = 0.0;
+  const double* zt = P.z + td.voff;
+  auto matvec_hook = [&](int k, const double* As, const double*) {
+    const double* zk = zt + 64 * k;
+#pragma unroll 4
+    for (int cb = 0; cb < 16; ++cb)
+      rhs_part = fma(As[(((w.warp << 4) + cb) << 5) + w.lane],
+                     zk[4 * cb + w.t], rhs_part);
+  };
+  acc_zero(acc);
+  stream_gemm<KMAJOR, KMAJOR>(
+      acc, max(j, 0),
+      [&](int k) {
+        const double* a = Lt + (size_t)tri_idx(i, k) * TILE_ELEMS;
+        return TilePair{a, a, 0, 16};
+      },
+      pipe, nullptr, nullptr, matvec_hook, w);
+  if (j >= 0) {
+    tile_mma<KMAJOR, KMAJOR>(acc, Ps, Ps, w);
+    matvec_hook(j, Ps, Ps);
+  }
+  splitk_exchange(acc, own, stA, w);
+  ktile_eval<KID, true>(own, xi, xi, P.d, DP, 64 * i, 64 * i, td.n, sv,
+                        nv + JITTER, w);
+
+  // dense copies for the in-CTA factorisation (alias the stage buffers)
+  constexpr int LD = 65;
+  double* Ls = stA;  // [64][65] A, then the unscaled columns of L
+  double* Xs = stB;  // [64][65] unscaled rows of L^{-1}
+#pragma unroll
+  for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        Ls[own_row(w, fi) * LD + own_col(w, fn, e)] = own[fi][fn][e];
+  // rhs = (y - m) - sum_k L(i,k) z_k
+  rhs_part += __shfl_xor_sync(0xffffffffu, rhs_part, 1);
+  rhs_part += __shfl_xor_sync(0xffffffffu, rhs_part, 2);
+  if (w.t == 0) {
+    const int r = 8 * w.warp + w.g;
+    const int gr = 64 * i + r;
+    const double yv = (gr < td.n) ? P.y[td.xoff + gr] - P.theta[TH_CONST] : 0.0;
+    vec[r] = yv - rhs_part;
+  }
+  __syncthreads();
+
+  // Fused unblocked Cholesky + triangular inverse, "unscaled" (LDL-like) form:
+  // thread (tr, tc) owns A[tr+16a][tc+16b] and B[tr+16a][tc+16b] (B starts as
+  // I and becomes L^{-1}); one barrier per column.
+  {
+    const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    double a_reg[4][4], b_reg[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        a_reg[a][b] = Ls[(tr + 16 * a) * LD + tc + 16 * b];
+        b_reg[a][b] = (tr + 16 * a == tc + 16 * b) ? 1.0 : 0.0;
+      }
+    __syncthreads();
+    for (int k = 0; k < 64; ++k) {
+      const int kq = k >> 4, kr = k & 15;
+      if (tc == kr) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b == kq) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) Ls[(tr + 16 * a) * LD + k] = a_reg[a][b];
+          }
+      }
+      if (tr == kr) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (a == kq) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) Xs[k * LD + tc + 16 * b] = b_reg[a][b];
+          }
+      }
+      __syncthreads();
+      const double pinv = 1.0 / Ls[k * LD + k];
+      double lr[4], lc[4], xr[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) lr[a] = Ls[(tr + 16 * a) * LD + k] * pinv;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        lc[b] = Ls[(tc + 16 * b) * LD + k];
+        xr[b] = Xs[k * LD + tc + 16 * b];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (16 * a + 15 <= k) continue;  // rows of this register block final
+        const int r = tr + 16 * a;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = tc + 16 * b;
+          if (r > k && c > k) a_reg[a][b] = fma(-lr[a], lc[b], a_reg[a][b]);
+          if (r > k && c <= k) b_reg[a][b] = fma(-lr[a], xr[b], b_reg[a][b]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // pivots -> 1/sqrt, log-determinant part, breakdown detection
+  double ld_part = 0.0;
+  if (threadIdx.x < 64) {
+    const double p = Ls[threadIdx.x * LD + threadIdx.x];
+    vec[64 + threadIdx.x] = 1.0 / sqrt(p);
+    ld_part = 0.5 * log(p);
+    const bool bad = !(p > 0.0);
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if (m && (threadIdx.x & 31) == 0)
+      atomicMin(&P.bad[blockIdx.y],
+                (unsigned)(64 * i + (threadIdx.x & 32) + __ffs(m)));
+  }
+  ld_part = block_sum(ld_part, red);
+  if (threadIdx.x == 0) P.logdet[td.voff / 64 + i] = ld_part;
+  // Ps may still be read by the L(i,j) bulk store
+  if (threadIdx.x == 0) bulk_wait_read_all();
+  __syncthreads();
+  const double* rs = vec + 64;
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
+    const int r = e >> 6, c = e & 63;
+    const int o = elem_off(r, c);
+    Cs[o] = (c <= r) ? Ls[r * LD + c] * rs[c] : 0.0;
+    Ps[o] = (c <= r) ? Xs[r * LD + c] * rs[r] : 0.0;
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bulk_s2g(Ltw + (size_t)tri_idx(i, i) * TILE_ELEMS, Cs, TILE_BYTES);
+    bulk_s2g(Mtw + (size_t)tri_idx(i, i) * TILE_ELEMS, Ps, TILE_BYTES);
+    bulk_commit();
+  }
+  // z_i = L(i,i)^{-1} rhs
+  {
+    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+    double s = 0.0;
+    for (int c = q; c <= r; c += 4) s = fma(Xs[r * LD + c], vec[c], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (q == 0) P.z[td.voff + 64 * i + r] = s * rs[r];
+  }
+  if (threadIdx.x == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------ alpha kernel --
+// alpha = M' z (= K~^{-1} r), block c per CTA; CTA c == 0 also finishes the
+// per-task NLL value  .5 z'z + sum log L_ii + .5 n log 2pi.
+__global__ void __launch_bounds__(NTHREADS) k_alpha(Params P) {
+  __shared__ double red[16];
+  __shared__ double part[8][64];
+  const TaskDesc td = P.tasks[blockIdx.y];
+  const int c = blockIdx.x;
+  if (c >= td.nblk) return;
+  const WarpPos w;
+  const double* Mt = P.Mt + td.tile_off * TILE_ELEMS;
+  const double* zt = P.z + td.voff;
+  // warp w handles row-blocks rb == w of every tile (k, c), k >= c; lane
+  // (g,t) accumulates column 4cb + t over rows 8rb + g.
+  double a16[16];
+#pragma unroll
+  for (int cb = 0; cb < 16; ++cb) a16[cb] = 0.0;
+  for (int k = c; k < (P.with_trtri ? td.nblk : 0); ++k) {
+    const double* tile = Mt + (size_t)tri_idx(k, c) * TILE_ELEMS;
+    const double zv = zt[64 * k + 8 * w.warp + w.g];
+#pragma unroll
+    for (int cb = 0; cb < 16; ++cb)
+      a16[cb] = fma(tile[(((w.warp << 4) + cb) << 5) + w.lane], zv, a16[cb]);
+  }
+  // reduce over g (lane bits 2..4), then over warps through smem
+#pragma unroll
+  for (int cb = 0; cb < 16; ++cb) {
+    double v = a16[cb];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (w.g == 0) part[w.warp][4 * cb + w.t] = v;
+  }
+  __syncthreads();
+  double av = 0.0;
+  if (threadIdx.x < 64) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) av += part[q][threadIdx.x];
+    P.alpha[td.voff + 64 * c + threadIdx.x] = av;
+  }
+  const double s = block_sum(threadIdx.x < 64 ? av : 0.0, red);
+  if (threadIdx.x == 0) P.asum[td.voff / 64 + c] = s;
+  if (c == 0) {
+    double zz = 0.0;
+    for (int e = threadIdx.x; e < 64 * td.nblk; e += NTHREADS)
+      zz = fma(zt[e], zt[e], zz);
+    zz = block_sum(zz, red);
+    if (threadIdx.x == 0) {
+      double ld = 0.0;
+      for (int b = 0; b < td.nblk; ++b) ld += P.logdet[td.voff / 64 + b];
+      const unsigned bad = P.bad[blockIdx.y];
+      double v = 0.5 * zz + ld + 0.5 * td.n * 1.8378770664093453;  // log(2 pi)
+      if (bad != 0xffffffffu) v = __longlong_as_double(0x7ff8000000000000LL);
+      P.info[blockIdx.y] = (bad != 0xffffffffu) ? (int)bad : 0;
+      P.nll_task[blockIdx.y] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------- lauum + gradient ---
+// CTA (task, tile (i,j)): S = (K~^{-1})(i,j) = sum_{k>=i} M(k,i)' M(k,j) on the
+// tensor pipe, then the gradient contraction of G = .5 (S - alpha alpha') with
+// dK/dtheta evaluated on the fly from X.  Partials per tile:
+//   [0] <G, K>   [1] tr G   [2+k] <G o W, ((x_k - x'_k)/l_k)^2>
+// (symmetric counterpart of an off-diagonal tile folded in by a factor 2).
+template <int KID>
+__global__ void __launch_bounds__(NTHREADS, 1) k_lauum_grad(Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TaskDesc td = P.tasks[blockIdx.y];
+  const int nblk = td.nblk;
+  const int ntile = nblk * (nblk + 1) / 2;
+  if ((int)blockIdx.x >= ntile) return;
+  int i = 0, j = blockIdx.x;  // tile slot -> (i, j); heavy (small i) first
+  while (j > i) { j -= i + 1; ++i; }
+
+  const WarpPos w;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+  double* stA = reinterpret_cast<double*>(smem + SM_STA);
+  double* stB = reinterpret_cast<double*>(smem + SM_STB);
+  double* vec = reinterpret_cast<double*>(smem + SL_VEC);
+  double* red2 = reinterpret_cast<double*>(smem + SL_RED2);
+  const int DP = xstride(P.d);
+  double* xi = reinterpret_cast<double*>(smem + SL_X);
+  double* xj = xi + 64 * DP;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
+              P.theta);
+  load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
+              P.theta);
+  if (threadIdx.x < 64) vec[threadIdx.x] = P.alpha[td.voff + 64 * i + threadIdx.x];
+  else if (threadIdx.x < 128)
+    vec[threadIdx.x] = P.alpha[td.voff + 64 * j + threadIdx.x - 64];
+  __syncthreads();
+  Pipe pipe{bars, stA, stB, 0u};
+  const double* Mt = P.Mt + td.tile_off * TILE_ELEMS;
+
+  double acc[4][4][2];
+  double own[2][4][2];
+  acc_zero(acc);
+  stream_gemm<MNMAJOR, MNMAJOR>(
+      acc, nblk - i,
+      [&](int kk) {
+        const int k = i + kk;
+        return TilePair{Mt + (size_t)tri_idx(k, i) * TILE_ELEMS,
+                        Mt + (size_t)tri_idx(k, j) * TILE_ELEMS, 0, 16};
+      },
+      pipe, nullptr, nullptr, NoHook(), w);
+  splitk_exchange(acc, own, stA, w);
+
+  const double sv = P.theta[TH_SV];
+  const double mult = (i == j) ? 1.0 : 2.0;
+  double g_sv = 0.0, g_nv = 0.0;
+  double gw[2][4][2];
+  {
+    double r2[2][4][2];
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) r2[fi][fn][0] = r2[fi][fn][1] = 0.0;
+    for (int k = 0; k < P.d; ++k) {
+      double xr[2], xc[4][2];
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi) xr[fi] = xi[own_row(w, fi) * DP + k];
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) xc[fn][e] = xj[own_col(w, fn, e) * DP + k];
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double df = xr[fi] - xc[fn][e];
+            r2[fi][fn][e] = fma(df, df, r2[fi][fn][e]);
+          }
+    }
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = own_row(w, fi), c = own_col(w, fn, e);
+          const int gr = 64 * i + r, gc = 64 * j + c;
+          double k, wg;
+          kern_eval<KID>(r2[fi][fn][e], sv, k, wg);
+          double G = 0.5 * (own[fi][fn][e] - vec[r] * vec[64 + c]);
+          if (gr >= td.n || gc >= td.n) G = 0.0;
+          g_sv = fma(mult * G, k, g_sv);
+          if (gr == gc) g_nv += G;
+          gw[fi][fn][e] = mult * G * wg;
+        }
+  }
+  // block-reduce the 2 + d partial sums deterministically
+  const int np = 2 + P.d;
+  for (int p = 0; p < np; ++p) {
+    double v;
+    if (p == 0) v = g_sv;
+    else if (p == 1) v = g_nv;
+    else {
+      const int k = p - 2;
+      v = 0.0;
+      double xr[2];
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi) xr[fi] = xi[own_row(w, fi) * DP + k];
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double xc = xj[own_col(w, fn, e) * DP + k];
+#pragma unroll
+          for (int fi = 0; fi < 2; ++fi) {
+            const double df = xr[fi] - xc;
+            v = fma(gw[fi][fn][e], df * df, v);
+          }
+        }
+    }
+    v = warp_sum(v);
+    if (w.lane == 0) red2[w.warp * GP_STRIDE + p] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < np) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NTHREADS / 32; ++q) s += red2[q * GP_STRIDE + threadIdx.x];
+    P.gpart[(td.tile_off + blockIdx.x) * GP_STRIDE + threadIdx.x] = s;
+  }
+}
+
+// per-task sum of the tile partials (fixed order -> deterministic)
+__global__ void k_reduce_task(Params P) {
+  const TaskDesc td = P.tasks[blockIdx.x];
+  const int ntile = td.nblk * (td.nblk + 1) / 2;
+  const int p = threadIdx.x;
+  if (p >= 2 + P.d) return;
+  double s = 0.0;
+  for (int t = 0; t < ntile; ++t) s += P.gpart[(td.tile_off + t) * GP_STRIDE + p];
+  P.gtask[(size_t)blockIdx.x * GP_STRIDE + p] = s;
+}
+
+// sums over tasks + chain rule.  out[0] = sum nll, out[1+p] = sum d nll/d raw_p,
+// out[1+P] = #non-empty tasks.  One CTA of 256 threads.
+__global__ void k_reduce_final(Params P, double* __restrict__ out,
+                               double* __restrict__ nll_task_out) {
+  __shared__ double red[16];
+  const int np = 3 + P.d;
+  const double sv = P.theta[TH_SV];
+  for (int q = 0; q <= np + 1; ++q) {
+    double v = 0.0;
+    for (int t = threadIdx.x; t < P.T; t += blockDim.x) {
+      const TaskDesc td = P.tasks[t];
+      if (td.n == 0) continue;
+      if (q == 0) v += P.nll_task[t];
+      else if (q == np + 1) v += 1.0;
+      else if (q == 1) {  // constant: -sum alpha
+        for (int b = 0; b < td.nblk; ++b) v -= P.asum[td.voff / 64 + b];
+      } else v += P.gtask[(size_t)t * GP_STRIDE + (q - 2)];
+    }
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) {
+      if (q >= 1 && q <= np) {
+        const int p = q - 1;
+        if (p == 1) v /= sv;                                    // <G,K>/sv
+        if (p >= 3) v *= P.theta[TH_INVLS + (p - 3)];           // /l_k
+        v *= P.theta[TH_CHAIN + p];
+      }
+      out[q] = v;
+    }
+  }
+  if (nll_task_out)
+    for (int t = threadIdx.x; t < P.T; t += blockDim.x)
+      nll_task_out[t] = P.tasks[t].n ? P.nll_task[t] : 0.0;
+}
+
+// optax.adam step with the accept / stop semantics of gp_utils/gp.py:135-146
+__global__ void k_adam(int P_, double* raw, double* m, double* v,
+                       double* accepted, const double* sums, double* scal,
+                       double lr, double b1, double b2, double eps) {
+  const int p = threadIdx.x;
+  const double cnt = sums[1 + P_];
+  const double loss = cnt > 0.0 ? sums[0] / cnt : 0.0;
+  const double t_old = scal[1];
+  const bool stopped = scal[2] != 0.0;
+  const bool fin = isfinite(loss);
+  __syncthreads();
+  if (p == 0) {
+    scal[0] = loss;
+    if (!stopped) {
+      if (fin) { scal[1] = t_old + 1.0; scal[3] += 1.0; }
+      else scal[2] = 1.0;
+    }
+  }
+  if (p < P_ && !stopped && fin) {
+    const double t = t_old + 1.0;
+    const double g = cnt > 0.0 ? sums[1 + p] / cnt : 0.0;
+    const double r0 = raw[p];
+    accepted[p] = r0;
+    const double mn = b1 * m[p] + (1.0 - b1) * g;
+    const double vn = b2 * v[p] + (1.0 - b2) * g * g;
+    m[p] = mn;
+    v[p] = vn;
+    const double mhat = mn / (1.0 - pow(b1, t));
+    const double vhat = vn / (1.0 - pow(b2, t));
+    raw[p] = r0 - lr * mhat / (sqrt(vhat) + eps);
+  }
+}
+
+// -------------------------------------------------- stand-alone Gram matrix --
+// kernel.covariance_matrix.matrix_map: out (n1, n2) row-major; HBM-write bound.
+template <int KID>
+__global__ void __launch_bounds__(NTHREADS) k_kernel_matrix(
+    const double* __restrict__ X1, long long n1, const double* __restrict__ X2,
+    long long n2, int d, const double* __restrict__ theta, int add_noise,
+    double jitter, double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int DP = xstride(d);
+  double* x1 = reinterpret_cast<double*>(smem);
+  double* x2 = x1 + 64 * DP;
+  const long long r0 = 64LL * blockIdx.y, c0 = 64LL * blockIdx.x;
+  load_xblock(x1, X1, r0, (int)min(64LL, n1 - r0), d, DP, theta);
+  load_xblock(x2, X2, c0, (int)min(64LL, n2 - c0), d, DP, theta);
+  __syncthreads();
+  const double sv = theta[TH_SV];
+  const double diag_add = add_noise ? theta[TH_NV] + jitter : 0.0;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double r2[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
+  for (int k = 0; k < d; ++k) {
+    double xr[4], xc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xr[a] = x1[(ty + 16 * a) * DP + k];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xc[b] = x2[(tx + 16 * b) * DP + k];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double df = xr[a] - xc[b];
+        r2[a][b] = fma(df, df, r2[a][b]);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const long long r = r0 + ty + 16 * a, c = c0 + tx + 16 * b;
+      if (r < n1 && c < n2) {
+        double k, wg;
+        kern_eval<KID>(r2[a][b], sv, k, wg);
+        if (r == c) k += diag_add;
+        out[r * n2 + c] = k;
+      }
+    }
+}
+
+__global__ void k_fill(double* out, long long n, const double* theta, int idx,
+                       double add) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = theta[idx] + add;
+}
+
+// packed L tiles -> row-major (n, n) lower factors with zeroed upper triangle
+__global__ void __launch_bounds__(NTHREADS) k_unpack_chol(Params P,
+                                                          double* __restrict__ out) {
+  const TaskDesc td = P.tasks[blockIdx.y];
+  const int ntile = td.nblk * (td.nblk + 1) / 2;
+  if ((int)blockIdx.x >= ntile) return;
+  int i = 0, j = blockIdx.x;
+  while (j > i) { j -= i + 1; ++i; }
+  const double* tile = P.Lt + (td.tile_off + blockIdx.x) * TILE_ELEMS;
+  double* o = out + td.chol_off;
+  const long long n = td.n;
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
+    const int r = e >> 6, c = e & 63;
+    const long long gr = 64LL * i + r, gc = 64LL * j + c;
+    if (gr < n && gc < n) {
+      o[gr * n + gc] = tile[elem_off(r, c)];
+      if (i != j) o[gc * n + gr] = 0.0;
+    }
+  }
+}
+
+// compact 64-padded per-task vectors into the caller's (sum n,) layout
+__global__ void k_unpad_vec(Params P, const double* __restrict__ src,
+                            double* __restrict__ dst) {
+  const TaskDesc td = P.tasks[blockIdx.y];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < td.n;
+       e += gridDim.x * blockDim.x)
+    dst[td.xoff + e] = src[td.voff + e];
+}
+
+__global__ void k_copy_scalars(const double* src, double* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void k_copy_info(const int* src, int* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ predict --
+// gp.predict (gp_utils/gp.py:242-305) against the cached M = L^{-1} tiles:
+//   K*  = k(X_obs, X_q)                      k_kstar   (tiles to L2-resident scratch)
+//   mu  = K*' alpha + m                      k_kstar   (partials per obs block)
+//   V   = L^{-1} K* = M K*                   k_predict_gemm (tensor pipe)
+//   var = k(xq,xq) - colsum(V o V)           k_predict_gemm / k_predict_final
+// followed by the acquisition epilogue (bo_utils/acfun.py:96-142).
+struct PredParams {
+  const double* X;      // (n, d) observations
+  const double* Xq;     // (nq, d) queries of this pass
+  const double* theta;
+  const double* Mt;     // cache: packed M tiles
+  const double* alpha;  // cache: 64-padded alpha
+  double* kst;          // scratch: [nqc][nblk] tiles
+  double* mupart;       // scratch: [nblk][nqc*64]
+  double* vpart;        // scratch: [nblk][nqc*64]
+  int n, nblk, d;
+  long long nq;
+  int nqc;
+};
+
+template <int KID>
+__global__ void __launch_bounds__(NTHREADS) k_kstar(PredParams Q) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* tile = reinterpret_cast<double*>(smem);
+  double* part = tile + TILE_ELEMS;          // [8][64]
+  double* al = part + 8 * 64;                // [64]
+  const int DP = xstride(Q.d);
+  double* xi = al + 64;
+  double* xj = xi + 64 * DP;
+  const int k = blockIdx.x, qc = blockIdx.y;
+  load_xblock(xi, Q.X, 64LL * k, min(64, Q.n - 64 * k), Q.d, DP, Q.theta);
+  load_xblock(xj, Q.Xq, 64LL * qc, (int)min(64LL, Q.nq - 64LL * qc), Q.d, DP,
+              Q.theta);
+  if (threadIdx.x < 64) al[threadIdx.x] = Q.alpha[64 * k + threadIdx.x];
+  __syncthreads();
+  const double sv = Q.theta[TH_SV];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double r2[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
+  for (int kk = 0; kk < Q.d; ++kk) {
+    double xr[4], xc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xr[a] = xi[(ty + 16 * a) * DP + kk];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xc[b] = xj[(tx + 16 * b) * DP + kk];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double df = xr[a] - xc[b];
+        r2[a][b] = fma(df, df, r2[a][b]);
+      }
+  }
+  double mu[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = ty + 16 * a, c = tx + 16 * b;
+      double kv, wg;
+      kern_eval<KID>(r2[a][b], sv, kv, wg);
+      if (64 * k + r >= Q.n) kv = 0.0;
+      tile[elem_off(r, c)] = kv;
+      mu[b] = fma(kv, al[r], mu[b]);
+    }
+  // reduce mu over the 16 ty values: lanes differ in ty by bit 4, then warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    double v = mu[b] + __shfl_xor_sync(0xffffffffu, mu[b], 16);
+    if (lane < 16) part[warp * 64 + tx + 16 * b] = v;
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bulk_s2g(Q.kst + ((size_t)qc * Q.nblk + k) * TILE_ELEMS, tile,
+             TILE_ELEMS * sizeof(double));
+    bulk_commit();
+  }
+  if (threadIdx.x < 64) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q * 64 + threadIdx.x];
+    Q.mupart[(size_t)k * Q.nqc * 64 + 64 * qc + threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) bulk_wait_all();
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_predict_gemm(PredParams Q) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int i = Q.nblk - 1 - blockIdx.x;  // heavy rows first
+  const int qc = blockIdx.y;
+  const WarpPos w;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+  double* stA = reinterpret_cast<double*>(smem + SM_STA);
+  double* stB = reinterpret_cast<double*>(smem + SM_STB);
+  double* part = reinterpret_cast<double*>(smem + SM_CS);  // [4][64]
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  Pipe pipe{bars, stA, stB, 0u};
+  double acc[4][4][2];
+  double own[2][4][2];
+  acc_zero(acc);
+  stream_gemm<KMAJOR, MNMAJOR>(
+      acc, i + 1,
+      [&](int k) {
+        return TilePair{Q.Mt + (size_t)tri_idx(i, k) * TILE_ELEMS,
+                        Q.kst + ((size_t)qc * Q.nblk + k) * TILE_ELEMS, 0, 16};
+      },
+      pipe, nullptr, nullptr, NoHook(), w);
+  splitk_exchange(acc, own, stA, w);
+  // column sums of V o V: reduce over fi, g (lane bits 2..4), then (wm, wk)
+#pragma unroll
+  for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = own[0][fn][e] * own[0][fn][e] + own[1][fn][e] * own[1][fn][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (w.g == 0) part[(w.wm * 2 + w.wk) * 64 + own_col(w, fn, e)] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 64)
+    Q.vpart[(size_t)i * Q.nqc * 64 + 64 * qc + threadIdx.x] =
+        part[threadIdx.x] + part[64 + threadIdx.x] + part[128 + threadIdx.x] +
+        part[192 + threadIdx.x];
+}
+
+// standard normal pdf / cdf as jax.scipy.stats.norm (acfun.py:109-110)
+__device__ __forceinline__ double acq_eval(int acq_id, double mu, double var,
+                                           double param) {
+  const double sd = sqrt(var);
+  if (acq_id == 3) return mu + param * sd;           // ucb_sub
+  const double gamma = (param - mu) / sd;
+  if (acq_id == 2) return -gamma;                    // probability_of_improvement_sub
+  const double pdf = 0.3989422804014327 * exp(-0.5 * gamma * gamma);
+  const double cdf = 0.5 * erfc(-gamma * 0.7071067811865476);
+  return (pdf - gamma * (1.0 - cdf)) * sd;           // expected_improvement_sub
+}
+
+__global__ void k_predict_final(PredParams Q, double noise_flag, double scale,
+                                int acq_id, double acq_param, double* mu_out,
+                                double* var_out, double* acq_out) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= Q.nq) return;
+  double mu = Q.theta[TH_CONST], v = 0.0;
+  const size_t ld = (size_t)Q.nqc * 64;
+  for (int k = 0; k < Q.nblk; ++k) {
+    mu += Q.mupart[k * ld + q];
+    v += Q.vpart[k * ld + q];
+  }
+  const double var = (Q.theta[TH_SV] - v + noise_flag * Q.theta[TH_NV]) * scale;
+  if (mu_out) mu_out[q] = mu;
+  if (var_out) var_out[q] = var;
+  if (acq_out) acq_out[q] = acq_eval(acq_id, mu, var, acq_param);
+}
+
+// prior prediction (no observations, gp.py:275-282) shares k_predict_final with
+// nblk = 0.  acfun_sub alone on given vectors:
+__global__ void k_acq(int acq_id, double param, long long nq, const double* mu,
+                      const double* var, double* out) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q < nq) out[q] = acq_eval(acq_id, mu[q], var[q], param);
+}
+
+}  // namespace hb

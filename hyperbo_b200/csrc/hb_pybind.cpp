@@ -1,0 +1,127 @@
+// Thin pybind11 layer over the C ABI (include/hyperbo_b200.h): forwards raw
+// device pointers (as integers), sizes and the CUDA stream.  No torch types, no
+// arithmetic -- the product is the C-ABI library this links against.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hyperbo_b200.h"
+
+namespace py = pybind11;
+using ptr_t = std::uintptr_t;
+
+namespace {
+
+inline void* P(ptr_t p) { return reinterpret_cast<void*>(p); }
+
+struct Handle {
+  hb_handle_t h = nullptr;
+  Handle(int device, int dtype) {
+    const int rc = hb_create(&h, device, dtype);
+    if (rc != HB_OK)
+      throw std::runtime_error("hb_create failed with status " +
+                               std::to_string(rc) +
+                               (rc == HB_ERR_NO_DEVICE ? " (no CUDA device)" : ""));
+  }
+  ~Handle() {
+    if (h) hb_destroy(h);
+  }
+  void check(int rc, const char* what) const {
+    if (rc == HB_OK) return;
+    const std::string msg = std::string(what) + ": status " + std::to_string(rc) +
+                            " (" + hb_last_error(h) + ")";
+    if (rc == HB_ERR_UNSUPPORTED) throw py::value_error(msg);  // -> mapped in Python
+    throw std::runtime_error(msg);
+  }
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "hyperbo_b200 C-ABI bindings";
+  m.def("version", [] { return std::string(hb_version()); });
+  m.attr("MAX_DIM") = HB_MAX_DIM;
+  m.attr("TILE") = HB_TILE;
+
+  py::class_<Handle>(m, "Handle")
+      .def(py::init<int, int>(), py::arg("device"), py::arg("dtype"))
+      .def("launch_count", [](Handle& s) { return hb_launch_count(s.h); })
+      .def("workspace_bytes", [](Handle& s) { return hb_workspace_bytes(s.h); })
+      .def("predictor_bytes",
+           [](Handle& s, int64_t n) { return hb_predictor_bytes(s.h, n); })
+      .def("kernel_matrix",
+           [](Handle& s, int kernel_id, ptr_t X1, int64_t n1, ptr_t X2, int64_t n2,
+              int d, ptr_t raw, uint32_t mask, int diag_only, int add_noise,
+              double jitter, ptr_t out, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_kernel_matrix(s.h, kernel_id, P(X1), n1, P(X2), n2, d,
+                                      P(raw), mask, diag_only, add_noise, jitter,
+                                      P(out), P(stream)),
+                     "hb_kernel_matrix");
+           })
+      .def("factorize_batched",
+           [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
+              int d, ptr_t X, ptr_t y, ptr_t raw, uint32_t mask, ptr_t chol,
+              ptr_t alpha, ptr_t nll, ptr_t info, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_factorize_batched(
+                         s.h, kernel_id, mean_id, (int)offs.size() - 1,
+                         offs.data(), d, P(X), P(y), P(raw), mask, P(chol),
+                         P(alpha), P(nll), (int32_t*)P(info), P(stream)),
+                     "hb_factorize_batched");
+           })
+      .def("nll_grad_batched",
+           [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
+              int d, ptr_t X, ptr_t y, ptr_t raw, uint32_t mask, ptr_t sums,
+              ptr_t nll_task, ptr_t info, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_nll_grad_batched(
+                         s.h, kernel_id, mean_id, (int)offs.size() - 1,
+                         offs.data(), d, P(X), P(y), P(raw), mask, P(sums),
+                         P(nll_task), (int32_t*)P(info), P(stream)),
+                     "hb_nll_grad_batched");
+           })
+      .def("adam_step",
+           [](Handle& s, int np, ptr_t raw, ptr_t mm, ptr_t vv, ptr_t accepted,
+              ptr_t sums, ptr_t scal, double lr, double b1, double b2, double eps,
+              ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_adam_step(s.h, np, P(raw), P(mm), P(vv), P(accepted),
+                                  P(sums), P(scal), lr, b1, b2, eps, P(stream)),
+                     "hb_adam_step");
+           })
+      .def("build_predictor",
+           [](Handle& s, int kernel_id, int mean_id, int64_t n, int d, ptr_t X,
+              ptr_t y, ptr_t raw, uint32_t mask, ptr_t cache, ptr_t chol,
+              ptr_t kinvy, ptr_t nll, ptr_t info, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_build_predictor(s.h, kernel_id, mean_id, n, d, P(X), P(y),
+                                        P(raw), mask, P(cache), P(chol), P(kinvy),
+                                        P(nll), (int32_t*)P(info), P(stream)),
+                     "hb_build_predictor");
+           })
+      .def("predict",
+           [](Handle& s, int kernel_id, int mean_id, int64_t n, int d, ptr_t X,
+              ptr_t cache, ptr_t raw, uint32_t mask, int64_t nq, ptr_t Xq,
+              double noise_flag, double var_scale, int acq_id, double acq_param,
+              ptr_t mu, ptr_t var, ptr_t acq, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_predict(s.h, kernel_id, mean_id, n, d, P(X), P(cache),
+                                P(raw), mask, nq, P(Xq), noise_flag, var_scale,
+                                acq_id, acq_param, P(mu), P(var), P(acq),
+                                P(stream)),
+                     "hb_predict");
+           })
+      .def("acquisition",
+           [](Handle& s, int acq_id, double param, int64_t nq, ptr_t mu, ptr_t var,
+              ptr_t out, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_acquisition(s.h, acq_id, param, nq, P(mu), P(var), P(out),
+                                    P(stream)),
+                     "hb_acquisition");
+           });
+}

@@ -1,0 +1,167 @@
+/*
+ * hyperbo_b200 -- C ABI of the B200-native GP pre-training / inference engine.
+ *
+ * This is the drop-in boundary.  google-research/hyperbo has no
+ * FFI of its own: its boundary is the function-level Python API, so every entry
+ * point below names the reference function (file:line under
+ * /root/reference/hyperbo/) whose arithmetic it replaces.  INTEGRATION.md shows
+ * the ctypes / pybind11 stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.
+ *  - every `const void*` / `void*` data pointer is a DEVICE pointer owned by the
+ *    caller, of the handle's scalar type (double for HB_F64, float for HB_F32);
+ *    `offs` arrays are HOST pointers.
+ *  - `stream` is the caller's cudaStream_t (passed as void*); all work is
+ *    enqueued asynchronously on it, nothing here synchronises the device.
+ *    (The first call with a new task shape set allocates workspace with
+ *    cudaMalloc; later calls with the same shapes do not, so the call sequence
+ *    is CUDA-graph capturable after one warm-up call.)
+ *  - return value: HB_OK or an HB_ERR_* code for API misuse only.  Numerical
+ *    breakdown (non-PD matrix) never raises: info[t] = failing column + 1 and
+ *    NaN propagates into nll / outputs, exactly like the reference, whose
+ *    Python loop then stops on the non-finite loss (gp_utils/gp.py:135-142).
+ *  - parameter vector layout (P = 3 + d scalars, handle dtype):
+ *        raw[0] = constant        (mean.constant,            mean.py:60-64)
+ *        raw[1] = signal_variance (kernel.py:78-81)
+ *        raw[2] = noise_variance  (linalg.py:64-68)
+ *        raw[3+k] = lengthscale[k], k < d   (ARD; kernel.py:80)
+ *    `warp_mask` bit p set  <=>  theta_p = softplus(raw_p) + 1e-10
+ *    (utils.DEFAULT_WARP_FUNC, gp_utils/utils.py:73-81); clear <=> identity
+ *    (warp_func=None, params_utils.py:97-111).
+ *  - ragged task batches: tasks are concatenated row-wise; task t owns rows
+ *    offs[t] .. offs[t+1]-1 of X (row-major, d columns) and y.  n_t = 0 is
+ *    allowed and skipped (objectives.py:184).
+ */
+#ifndef HYPERBO_B200_H_
+#define HYPERBO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_handle_s* hb_handle_t;
+
+enum hb_status {
+  HB_OK = 0,
+  HB_ERR_BAD_ARG = 1,      /* null pointer, bad id, negative size */
+  HB_ERR_UNSUPPORTED = 2,  /* d > HB_MAX_DIM, unsupported dtype/kernel combo */
+  HB_ERR_CUDA = 3,         /* a CUDA runtime call failed (see hb_last_error) */
+  HB_ERR_NO_DEVICE = 4
+};
+
+enum hb_dtype { HB_F64 = 0, HB_F32 = 1 };
+
+/* gp_utils/kernel.py:63-123 */
+enum hb_kernel { HB_KERNEL_SE = 0, HB_KERNEL_MATERN32 = 1, HB_KERNEL_MATERN52 = 2 };
+/* gp_utils/mean.py:54-64 */
+enum hb_mean { HB_MEAN_ZERO = 0, HB_MEAN_CONSTANT = 1 };
+/* bo_utils/acfun.py:96-142 */
+enum hb_acq { HB_ACQ_NONE = 0, HB_ACQ_EI = 1, HB_ACQ_PI = 2, HB_ACQ_UCB = 3 };
+
+#define HB_MAX_DIM 32
+#define HB_TILE 64 /* edge of the packed lower-triangular tiles */
+
+/* ---- lifetime ----------------------------------------------------------- */
+/* One handle per device per host thread; owns the workspace arena.          */
+int hb_create(hb_handle_t* out, int device, int dtype);
+int hb_destroy(hb_handle_t h);
+const char* hb_last_error(hb_handle_t h);
+const char* hb_version(void);
+/* Number of kernel launches this handle has enqueued (bench `gpu_launches`). */
+int64_t hb_launch_count(hb_handle_t h);
+/* Bytes of device workspace currently held. */
+int64_t hb_workspace_bytes(hb_handle_t h);
+
+/* ---- a4-a7: Gram / cross-Gram ------------------------------------------- */
+/* kernel.covariance_matrix.matrix_map (gp_utils/kernel.py:33-58) for
+ * squared_exponential / matern32 / matern52 (kernel.py:63-123), optionally
+ * followed by  + I*(noise_variance + jitter)  (linalg.compute_delta_y_and_cov,
+ * basics/linalg.py:64-68) when add_noise != 0 and X2 == NULL.
+ * out: (n1, n2) row-major; or (n1,) when diag_only != 0 and X2 == NULL
+ * (kernel.py:54-56 -- diag is ignored when X2 is given). */
+int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,
+                     const void* X2_or_null, int64_t n2, int d,
+                     const void* raw, uint32_t warp_mask, int diag_only,
+                     int add_noise, double jitter, void* out, void* stream);
+
+/* ---- a7-a10: batched factorisation + per-task NLL ----------------------- */
+/* linalg.solve_gp_linear_system (basics/linalg.py:72-110) for every task, plus
+ * objectives.neg_log_marginal_likelihood's per-task value
+ * (gp_utils/objectives.py:144-156):
+ *   K~_t = K(X_t,X_t) + (noise_variance + 1e-6) I,  L_t = chol(K~_t),
+ *   alpha_t = K~_t^{-1} (y_t - m),  nll_t = .5 r'alpha + sum log L_ii + .5 n log 2pi.
+ * chol_out_or_null: concatenated row-major (n_t, n_t) lower factors with the
+ *   strict upper triangle zeroed (== jspla.cholesky(lower=True)), task t at
+ *   element offset sum_{s<t} n_s^2.
+ * alpha_out_or_null: (sum n,)  nll_out_or_null: (T,)  info_out_or_null: (T,) int32. */
+int hb_factorize_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
+                         const int64_t* offs_host, int d, const void* X,
+                         const void* y, const void* raw, uint32_t warp_mask,
+                         void* chol_out_or_null, void* alpha_out_or_null,
+                         void* nll_out_or_null, int32_t* info_out_or_null,
+                         void* stream);
+
+/* ---- a10: batched NLL + gradient w.r.t. the raw parameters -------------- */
+/* What jax.value_and_grad(loss_func) computes at gp_utils/gp.py:134 for
+ * objective = neg_log_marginal_likelihood, restated in closed form
+ * (G_t = .5 (K~^{-1} - alpha alpha')), as SUMS over the tasks of this call so
+ * that task shards on several GPUs combine with one all-reduce(sum):
+ *   sums_out[0]        = sum_t nll_t
+ *   sums_out[1 + p]    = sum_t d nll_t / d raw_p     (p < P = 3 + d)
+ *   sums_out[1 + P]    = number of non-empty tasks
+ * sums_out has P + 2 scalars.  nll_task_out_or_null: (T,) per-task nll
+ * (return_key2nll, objectives.py:208-209). */
+int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
+                        const int64_t* offs_host, int d, const void* X,
+                        const void* y, const void* raw, uint32_t warp_mask,
+                        void* sums_out, void* nll_task_out_or_null,
+                        int32_t* info_out_or_null, void* stream);
+
+/* ---- a11: one optax.adam update (gp_utils/gp.py:124,143-144) ------------ */
+/* state (device, handle dtype): raw[P], m[P], v[P], accepted[P].
+ * scalars_io (device, 4 scalars): [0] loss of this step (written),
+ *   [1] step counter t (read, incremented), [2] stopped flag (0/1),
+ *   [3] number of accepted steps.
+ * Semantics of gp.py:135-146: loss = sums[0]/sums[1+P]; if finite:
+ * accepted <- raw, then raw <- raw - lr*mhat/(sqrt(vhat)+eps); else stopped=1
+ * and nothing changes any more (the host loop `break`s). */
+int hb_adam_step(hb_handle_t h, int P, void* raw, void* m, void* v,
+                 void* accepted, const void* sums, void* scalars_io, double lr,
+                 double b1, double b2, double eps, void* stream);
+
+/* ---- a12/a13: predictor cache, predict, acquisition --------------------- */
+/* Bytes of the opaque predictor cache for n observations (packed L^{-1} tiles,
+ * alpha, padded).  */
+int64_t hb_predictor_bytes(hb_handle_t h, int64_t n);
+/* GP.setup_predictor (gp_utils/gp.py:540-560): factorise one task and fill the
+ * caller-owned cache; optionally also emit the reference-visible GPCache fields
+ * chol (n,n) row-major lower and kinvy (n,). */
+int hb_build_predictor(hb_handle_t h, int kernel_id, int mean_id, int64_t n,
+                       int d, const void* X, const void* y, const void* raw,
+                       uint32_t warp_mask, void* cache, void* chol_out_or_null,
+                       void* kinvy_out_or_null, void* nll_out_or_null,
+                       int32_t* info_out_or_null, void* stream);
+/* gp.predict (gp_utils/gp.py:242-305, full_cov=False) + GP.predict's noise /
+ * N/(N-1) handling (gp.py:607-619) + acfun_sub (bo_utils/acfun.py:96-142):
+ *   mu_q  = K*' alpha + m
+ *   var_q = (k(xq,xq) - |L^{-1} K*_q|^2 + noise_add) * var_scale
+ *   acq_q = acfun_sub(mu_q, sqrt(var_q), acq_param)        (if acq_id != NONE)
+ * Outputs (nq,) each; any of mu/var/acq may be NULL. */
+int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
+               const void* X, const void* cache, const void* raw,
+               uint32_t warp_mask, int64_t nq, const void* Xq,
+               double noise_add_flag, double var_scale, int acq_id,
+               double acq_param, void* mu_out, void* var_out, void* acq_out,
+               void* stream);
+/* acfun_sub alone on given mu / var vectors (bo_utils/acfun.py:96-142). */
+int hb_acquisition(hb_handle_t h, int acq_id, double acq_param, int64_t nq,
+                   const void* mu, const void* var, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERBO_B200_H_ */
