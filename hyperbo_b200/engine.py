@@ -1,0 +1,257 @@
+"""Host-side driver of the C-ABI engine: device memory and streams come from
+PyTorch (plumbing); all arithmetic happens in libhyperbo_b200.so.
+
+There is NO CPU fallback: constructing an Engine without the CUDA extension or
+without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+KERNEL_IDS = {"squared_exponential": 0, "matern32": 1, "matern52": 2}
+MEAN_IDS = {"zero": 0, "constant": 1}
+ACQ_IDS = {"none": 0, "ei": 1, "pi": 2, "ucb": 3}
+DTYPES = {torch.float64: 0, torch.float32: 1}
+JITTER = 1e-6  # basics/linalg.py:42 of the reference
+
+_lock = threading.Lock()
+_engines: Dict[Tuple[int, torch.dtype], "Engine"] = {}
+
+
+def _load_ext():
+  try:
+    from hyperbo_b200 import _C  # type: ignore
+  except ImportError as e:  # fail loudly: no silent eager fallback
+    raise RuntimeError(
+        "hyperbo_b200._C (the CUDA extension) is not built; run "
+        "`python -c 'import __graft_entry__ as g; g.build()'` or "
+        "`python hyperbo_b200/_build.py`") from e
+  return _C
+
+
+class PackedDataset:
+  """Ragged task batch in the C-ABI layout: rows of all non-empty, non-aligned
+  tasks concatenated; offs = prefix sums (host list)."""
+
+  def __init__(self, keys, x: torch.Tensor, y: torch.Tensor, offs: List[int]):
+    self.keys = list(keys)
+    self.x = x
+    self.y = y
+    self.offs = [int(o) for o in offs]
+
+  @property
+  def num_tasks(self) -> int:
+    return len(self.offs) - 1
+
+  @property
+  def d(self) -> int:
+    return int(self.x.shape[1])
+
+
+class Engine:
+  """One C-ABI handle per (device, dtype)."""
+
+  def __init__(self, device: Optional[int] = None, dtype=torch.float64):
+    if not torch.cuda.is_available():
+      raise RuntimeError("hyperbo_b200 needs a CUDA device (no CPU fallback)")
+    self._C = _load_ext()
+    if device is None:
+      device = torch.cuda.current_device()
+    self.device_index = int(device)
+    self.device = torch.device("cuda", self.device_index)
+    self.dtype = dtype
+    with torch.cuda.device(self.device):
+      self.h = self._C.Handle(self.device_index, DTYPES[dtype])
+    self.max_dim = self._C.MAX_DIM
+
+  # ------------------------------------------------------------- helpers --
+  @staticmethod
+  def get(device: Optional[int] = None, dtype=torch.float64) -> "Engine":
+    if device is None:
+      if not torch.cuda.is_available():
+        raise RuntimeError("hyperbo_b200 needs a CUDA device (no CPU fallback)")
+      device = torch.cuda.current_device()
+    key = (int(device), dtype)
+    with _lock:
+      if key not in _engines:
+        _engines[key] = Engine(device, dtype)
+      return _engines[key]
+
+  def _stream(self) -> int:
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def tensor(self, a, shape=None) -> torch.Tensor:
+    t = torch.as_tensor(a)
+    t = t.to(device=self.device, dtype=self.dtype)
+    if shape is not None:
+      t = t.reshape(shape)
+    return t.contiguous()
+
+  def launch_count(self) -> int:
+    return int(self.h.launch_count())
+
+  def workspace_bytes(self) -> int:
+    return int(self.h.workspace_bytes())
+
+  def _check_dim(self, d):
+    if d > self.max_dim:
+      raise NotImplementedError(
+          f"input dimension {d} > {self.max_dim} is not supported by the engine")
+
+  # --------------------------------------------------------------- packing --
+  def pack(self, tasks: Sequence[Tuple[object, torch.Tensor, torch.Tensor]]
+           ) -> PackedDataset:
+    """tasks: iterable of (key, x (n,d), y (n,1) or (n,)).  Empty tasks are
+    dropped (objectives.py:184 of the reference)."""
+    keys, xs, ys, offs = [], [], [], [0]
+    for k, x, y in tasks:
+      x = self.tensor(x)
+      if x.shape[0] == 0:
+        continue
+      y = self.tensor(y).reshape(-1)
+      if y.shape[0] != x.shape[0]:
+        raise ValueError(f"dataset[{k}].x has shape {tuple(x.shape)} but y has "
+                         f"{y.shape[0]} rows")
+      keys.append(k)
+      xs.append(x)
+      ys.append(y)
+      offs.append(offs[-1] + x.shape[0])
+    if not xs:
+      return PackedDataset([], torch.zeros((0, 1), device=self.device,
+                                           dtype=self.dtype),
+                           torch.zeros((0,), device=self.device,
+                                       dtype=self.dtype), [0])
+    x = torch.cat(xs, 0).contiguous()
+    self._check_dim(x.shape[1])
+    return PackedDataset(keys, x, torch.cat(ys, 0).contiguous(), offs)
+
+  # ------------------------------------------------------------ operations --
+  def kernel_matrix(self, kernel_id: int, x1, x2, raw, mask: int, diag=False,
+                    add_noise=False, jitter=JITTER) -> torch.Tensor:
+    x1 = self.tensor(x1)
+    n1, d = x1.shape
+    self._check_dim(d)
+    raw = self.tensor(raw)
+    if x2 is None:
+      if diag:
+        out = torch.empty((n1,), device=self.device, dtype=self.dtype)
+      else:
+        out = torch.empty((n1, n1), device=self.device, dtype=self.dtype)
+      self.h.kernel_matrix(kernel_id, x1.data_ptr(), n1, 0, 0, d,
+                           raw.data_ptr(), mask, int(diag), int(add_noise),
+                           float(jitter), out.data_ptr(), self._stream())
+      return out
+    x2 = self.tensor(x2)
+    n2 = x2.shape[0]
+    out = torch.empty((n1, n2), device=self.device, dtype=self.dtype)
+    self.h.kernel_matrix(kernel_id, x1.data_ptr(), n1, x2.data_ptr(), n2, d,
+                         raw.data_ptr(), mask, 0, 0, float(jitter),
+                         out.data_ptr(), self._stream())
+    return out
+
+  def factorize(self, kernel_id: int, mean_id: int, ds: PackedDataset, raw,
+                mask: int, want_chol=True, want_alpha=True):
+    """-> (chol list or None, alpha (sum n,) or None, nll (T,), info (T,))."""
+    raw = self.tensor(raw)
+    T = ds.num_tasks
+    ns = [ds.offs[t + 1] - ds.offs[t] for t in range(T)]
+    chol = torch.empty((sum(n * n for n in ns),), device=self.device,
+                       dtype=self.dtype) if want_chol else None
+    alpha = torch.empty((ds.offs[-1],), device=self.device,
+                        dtype=self.dtype) if want_alpha else None
+    nll = torch.zeros((max(T, 1),), device=self.device, dtype=self.dtype)
+    info = torch.zeros((max(T, 1),), device=self.device, dtype=torch.int32)
+    self.h.factorize_batched(
+        kernel_id, mean_id, ds.offs, ds.d, ds.x.data_ptr(), ds.y.data_ptr(),
+        raw.data_ptr(), mask, chol.data_ptr() if want_chol else 0,
+        alpha.data_ptr() if want_alpha else 0, nll.data_ptr(), info.data_ptr(),
+        self._stream())
+    chols = None
+    if want_chol:
+      chols, o = [], 0
+      for n in ns:
+        chols.append(chol[o:o + n * n].view(n, n))
+        o += n * n
+    return chols, alpha, nll[:T], info[:T]
+
+  def nll_grad(self, kernel_id: int, mean_id: int, ds: PackedDataset, raw,
+               mask: int, sums_out: Optional[torch.Tensor] = None,
+               want_task_nll=False):
+    """-> sums (P+2,) = [sum nll, sum d/d raw_p ..., count] (+ per-task nll)."""
+    raw = self.tensor(raw)
+    P = 3 + ds.d
+    if sums_out is None:
+      sums_out = torch.empty((P + 2,), device=self.device, dtype=self.dtype)
+    T = ds.num_tasks
+    nll_task = torch.zeros((max(T, 1),), device=self.device,
+                           dtype=self.dtype) if want_task_nll else None
+    self.h.nll_grad_batched(
+        kernel_id, mean_id, ds.offs, ds.d, ds.x.data_ptr(), ds.y.data_ptr(),
+        raw.data_ptr(), mask, sums_out.data_ptr(),
+        nll_task.data_ptr() if want_task_nll else 0, 0, self._stream())
+    if want_task_nll:
+      return sums_out, nll_task[:T]
+    return sums_out
+
+  def adam_step(self, P: int, raw, m, v, accepted, sums, scal, lr, b1=0.9,
+                b2=0.999, eps=1e-8):
+    self.h.adam_step(P, raw.data_ptr(), m.data_ptr(), v.data_ptr(),
+                     accepted.data_ptr(), sums.data_ptr(), scal.data_ptr(),
+                     float(lr), float(b1), float(b2), float(eps),
+                     self._stream())
+
+  def build_predictor(self, kernel_id: int, mean_id: int, x, y, raw, mask: int):
+    """-> (cache bytes tensor, chol (n,n), kinvy (n,1), nll scalar, info)."""
+    x = self.tensor(x)
+    n, d = x.shape
+    self._check_dim(d)
+    y = self.tensor(y).reshape(-1)
+    raw = self.tensor(raw)
+    nbytes = int(self.h.predictor_bytes(n))
+    cache = torch.empty((nbytes // 8,), device=self.device, dtype=torch.float64)
+    chol = torch.empty((n, n), device=self.device, dtype=self.dtype)
+    kinvy = torch.empty((n, 1), device=self.device, dtype=self.dtype)
+    nll = torch.zeros((1,), device=self.device, dtype=self.dtype)
+    info = torch.zeros((1,), device=self.device, dtype=torch.int32)
+    self.h.build_predictor(kernel_id, mean_id, n, d, x.data_ptr(), y.data_ptr(),
+                           raw.data_ptr(), mask, cache.data_ptr(),
+                           chol.data_ptr(), kinvy.data_ptr(), nll.data_ptr(),
+                           info.data_ptr(), self._stream())
+    return cache, chol, kinvy, nll, info
+
+  def predict(self, kernel_id: int, mean_id: int, x, cache, raw, mask: int, xq,
+              noise_flag=0.0, var_scale=1.0, acq_id=0, acq_param=0.0,
+              want_mu=True, want_var=True):
+    xq = self.tensor(xq)
+    nq, d = xq.shape
+    self._check_dim(d)
+    raw = self.tensor(raw)
+    if x is None or x.shape[0] == 0:
+      n, xp, cp = 0, 0, 0
+    else:
+      x = self.tensor(x)
+      n, xp, cp = x.shape[0], x.data_ptr(), cache.data_ptr()
+    mu = torch.empty((nq, 1), device=self.device,
+                     dtype=self.dtype) if want_mu else None
+    var = torch.empty((nq, 1), device=self.device,
+                      dtype=self.dtype) if want_var else None
+    acq = torch.empty((nq, 1), device=self.device,
+                      dtype=self.dtype) if acq_id else None
+    self.h.predict(kernel_id, mean_id, n, d, xp, cp, raw.data_ptr(), mask, nq,
+                   xq.data_ptr(), float(noise_flag), float(var_scale), acq_id,
+                   float(acq_param), mu.data_ptr() if want_mu else 0,
+                   var.data_ptr() if want_var else 0,
+                   acq.data_ptr() if acq_id else 0, self._stream())
+    return mu, var, acq
+
+  def acquisition(self, acq_id: int, param: float, mu, var) -> torch.Tensor:
+    mu = self.tensor(mu).reshape(-1)
+    var = self.tensor(var).reshape(-1)
+    out = torch.empty_like(mu)
+    self.h.acquisition(acq_id, float(param), mu.shape[0], mu.data_ptr(),
+                       var.data_ptr(), out.data_ptr(), self._stream())
+    return out.reshape(-1, 1)
