@@ -453,7 +453,8 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
 
 int hb_adam_step(hb_handle_t h, int P_, void* raw, void* m, void* v,
                  void* accepted, const void* sums, void* scalars_io, double lr,
-                 double b1, double b2, double eps, void* stream) {
+                 double b1, double b2, double eps, int tie_lengthscale,
+                 void* stream) {
   if (!h) return HB_ERR_BAD_ARG;
   if (h->dtype != HB_F64) return fail(h, HB_ERR_UNSUPPORTED, "dtype");
   if (P_ < 1 || P_ > 3 + MAX_DIM || !raw || !m || !v || !accepted || !sums ||
@@ -462,7 +463,8 @@ int hb_adam_step(hb_handle_t h, int P_, void* raw, void* m, void* v,
   k_adam<<<1, 64, 0, (cudaStream_t)stream>>>(P_, (double*)raw, (double*)m,
                                             (double*)v, (double*)accepted,
                                             (const double*)sums,
-                                            (double*)scalars_io, lr, b1, b2, eps);
+                                            (double*)scalars_io, lr, b1, b2, eps,
+                                            tie_lengthscale);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

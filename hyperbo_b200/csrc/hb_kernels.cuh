@@ -708,7 +708,7 @@ __global__ void k_reduce_final(Params P, double* __restrict__ out,
 // optax.adam step with the accept / stop semantics of gp_utils/gp.py:135-146
 __global__ void k_adam(int P_, double* raw, double* m, double* v,
                        double* accepted, const double* sums, double* scal,
-                       double lr, double b1, double b2, double eps) {
+                       double lr, double b1, double b2, double eps, int tie_ls) {
   const int p = threadIdx.x;
   const double cnt = sums[1 + P_];
   const double loss = cnt > 0.0 ? sums[0] / cnt : 0.0;
@@ -725,7 +725,12 @@ __global__ void k_adam(int P_, double* raw, double* m, double* v,
   }
   if (p < P_ && !stopped && fin) {
     const double t = t_old + 1.0;
-    const double g = cnt > 0.0 ? sums[1 + p] / cnt : 0.0;
+    double g = cnt > 0.0 ? sums[1 + p] / cnt : 0.0;
+    if (tie_ls && p >= 3) {
+      g = 0.0;
+      for (int k = 3; k < P_; ++k) g += sums[1 + k];
+      g = cnt > 0.0 ? g / cnt : 0.0;
+    }
     const double r0 = raw[p];
     accepted[p] = r0;
     const double mn = b1 * m[p] + (1.0 - b1) * g;

@@ -88,10 +88,11 @@ PYBIND11_MODULE(_C, m) {
       .def("adam_step",
            [](Handle& s, int np, ptr_t raw, ptr_t mm, ptr_t vv, ptr_t accepted,
               ptr_t sums, ptr_t scal, double lr, double b1, double b2, double eps,
-              ptr_t stream) {
+              int tie_ls, ptr_t stream) {
              py::gil_scoped_release rel;
              s.check(hb_adam_step(s.h, np, P(raw), P(mm), P(vv), P(accepted),
-                                  P(sums), P(scal), lr, b1, b2, eps, P(stream)),
+                                  P(sums), P(scal), lr, b1, b2, eps, tie_ls,
+                                  P(stream)),
                      "hb_adam_step");
            })
       .def("build_predictor",

@@ -198,11 +198,11 @@ class Engine:
     return sums_out
 
   def adam_step(self, P: int, raw, m, v, accepted, sums, scal, lr, b1=0.9,
-                b2=0.999, eps=1e-8):
+                b2=0.999, eps=1e-8, tie_lengthscale=False):
     self.h.adam_step(P, raw.data_ptr(), m.data_ptr(), v.data_ptr(),
                      accepted.data_ptr(), sums.data_ptr(), scal.data_ptr(),
                      float(lr), float(b1), float(b2), float(eps),
-                     self._stream())
+                     int(bool(tie_lengthscale)), self._stream())
 
   def build_predictor(self, kernel_id: int, mean_id: int, x, y, raw, mask: int):
     """-> (cache bytes tensor, chol (n,n), kinvy (n,1), nll scalar, info)."""

@@ -1,0 +1,516 @@
+"""Inference and prediction for a (multi-task) GP -- mirrors
+hyperbo/gp_utils/gp.py (infer_parameters :53-195, predict :242-305, GP :308-620)
+with the per-task hot path running in the B200 engine.
+
+Differences forced by the platform (documented in DESIGN.md):
+  * arrays are torch CUDA float64 tensors; `key` arguments are int seeds or
+    torch.Generators (jax.random does not exist here);
+  * the objective must be the NLL (callable `objectives.nll` /
+    `objectives.neg_log_marginal_likelihood` or the strings 'nll' /
+    'neg_log_marginal_likelihood'); method must be 'adam'.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from hyperbo_b200 import engine as _engine
+from hyperbo_b200.basics import data_utils
+from hyperbo_b200.basics import definitions as defs
+from hyperbo_b200.basics import linalg
+from hyperbo_b200.basics import params_utils
+from hyperbo_b200.gp_utils import kernel as _kernel
+from hyperbo_b200.gp_utils import mean as _mean
+from hyperbo_b200.gp_utils import objectives as obj
+
+retrieve_params = params_utils.retrieve_params
+
+GPCache = defs.GPCache
+SubDataset = defs.SubDataset
+GPParams = defs.GPParams
+
+
+def _is_nll(objective) -> bool:
+  return objective in (obj.neg_log_marginal_likelihood, obj.nll, "nll",
+                       "neg_log_marginal_likelihood")
+
+
+def _dist_world():
+  import torch.distributed as dist
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(), dist.get_world_size()
+  return 0, 1
+
+
+class AdamTrainer:
+  """Device-resident Adam loop state for gp.infer_parameters (gp.py:114-157).
+
+  One `step()` = batched NLL + gradient over this rank's task shard
+  (hb_nll_grad_batched), one all-reduce(sum) of the P+2 partial sums when
+  several ranks share the dataset, and one optax.adam update (hb_adam_step).
+  Parameters and optimiser state never leave the device; `loss()` is the one
+  host read the reference's isfinite check needs.
+  """
+
+  def __init__(self, eng, kid, mid, raw_init, mask, d, lr, b1=0.9, b2=0.999,
+               eps=1e-8, allreduce=False, tie_lengthscale=False):
+    self.eng, self.kid, self.mid, self.mask, self.d = eng, kid, mid, mask, d
+    self.P = 3 + d
+    self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
+    dev, dt = eng.device, eng.dtype
+    self.raw = eng.tensor(raw_init).clone()
+    self.m = torch.zeros(self.P, device=dev, dtype=dt)
+    self.v = torch.zeros(self.P, device=dev, dtype=dt)
+    self.accepted = self.raw.clone()
+    self.sums = torch.zeros(self.P + 2, device=dev, dtype=dt)
+    self.scal = torch.zeros(4, device=dev, dtype=dt)
+    self.allreduce = allreduce
+    self.tie_lengthscale = tie_lengthscale
+    self._graph = None
+    self._graph_ds = None
+
+  def _enqueue(self, ds):
+    self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
+                      sums_out=self.sums)
+    if self.allreduce:
+      import torch.distributed as dist
+      dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)
+    self.eng.adam_step(self.P, self.raw, self.m, self.v, self.accepted,
+                       self.sums, self.scal, self.lr, self.b1, self.b2,
+                       self.eps, self.tie_lengthscale)
+
+  def step(self, ds, use_graph=False):
+    """Enqueue one optimiser step on the current stream."""
+    if not use_graph or self.allreduce:
+      self._enqueue(ds)
+      return
+    if self._graph is None or self._graph_ds is not ds:
+      # warm up (allocates workspace), then capture the launch sequence
+      s = torch.cuda.Stream(device=self.eng.device)
+      s.wait_stream(torch.cuda.current_stream(self.eng.device))
+      state = [t.clone() for t in (self.raw, self.m, self.v, self.accepted,
+                                   self.scal)]
+      with torch.cuda.stream(s):
+        self._enqueue(ds)
+      torch.cuda.current_stream(self.eng.device).wait_stream(s)
+      torch.cuda.synchronize(self.eng.device)
+      for t, c in zip((self.raw, self.m, self.v, self.accepted, self.scal),
+                      state):
+        t.copy_(c)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._enqueue(ds)
+      for t, c in zip((self.raw, self.m, self.v, self.accepted, self.scal),
+                      state):
+        t.copy_(c)
+      self._graph, self._graph_ds = g, ds
+    self._graph.replay()
+
+  def loss(self) -> float:
+    return float(self.scal[0])  # device -> host sync (gp.py:135-138)
+
+  @property
+  def stopped(self) -> bool:
+    return bool(self.scal[2] != 0)
+
+
+def shard_tasks(items: List, rank: int, world: int) -> List:
+  """Round-robin task shard  t = rank (mod world)  (SURVEY.md 8e)."""
+  return [it for t, it in enumerate(items) if t % world == rank]
+
+
+def infer_parameters(mean_func,
+                     cov_func,
+                     init_params,
+                     dataset,
+                     warp_func=None,
+                     objective=obj.neg_log_marginal_likelihood,
+                     key=None,
+                     get_params_path=None,
+                     callback=None):
+  """Posterior inference for a meta GP (gp.py:53-195, Adam branch :114-157).
+
+  When torch.distributed is initialised with world_size > 1, every rank passes
+  the SAME dataset; tasks are sharded round-robin across ranks and the partial
+  sums are combined with one all-reduce per step, so all ranks return identical
+  parameters.
+  """
+  if get_params_path is not None and get_params_path() is not None:
+    raise NotImplementedError("saving params to a path (params_utils.py:45-87)")
+  if key is None:
+    key = 0
+    logging.info("Using default random state in infer_parameters.")
+  if not dataset:
+    logging.info("No dataset present to train GP.")
+    return init_params
+  params = init_params
+  method = params.config["method"]
+  batch_size = params.config["batch_size"]
+  max_training_step = init_params.config["max_training_step"]
+  if max_training_step <= 0 and method != "slice_sample":
+    return init_params
+  if method != "adam":
+    if method in ("lbfgs", "bfgs"):
+      raise NotImplementedError(
+          f"method '{method}' (host-side quasi-Newton drivers, gp.py:158-191) "
+          "is a 'next' row; use objectives.nll_value_and_grad with your own "
+          "driver, or method='adam'")
+    raise ValueError(f"Optimization method {method} is not supported.")
+  if not _is_nll(objective):
+    raise NotImplementedError(
+        "the engine trains with objective = neg_log_marginal_likelihood only")
+  if "priors" in params.config:
+    raise NotImplementedError("log-prior terms (objectives.py:197-207)")
+
+  kid = _kernel.kernel_id_of(cov_func)
+  mid = _mean.mean_id_of(mean_func)
+  eng = _engine.Engine.get()
+  rank, world = _dist_world()
+
+  def pack(batch):
+    items = obj._select(batch, exclude_aligned=True)  # pylint: disable=protected-access
+    return eng.pack(shard_tasks(items, rank, world))
+
+  # data_utils.sub_sample_dataset_iterator only changes tasks with
+  # n >= batch_size; when none qualifies the batch is the dataset every step.
+  dataset = {k: SubDataset(*v) for k, v in dataset.items()}
+  needs_subsample = any(
+      torch.as_tensor(s.x).shape[0] >= batch_size for s in dataset.values())
+  dataset_iter = data_utils.sub_sample_dataset_iterator(key, dataset,
+                                                        batch_size)
+  static_ds = None if needs_subsample else pack(dataset)
+  any_x = next(iter(dataset.values())).x
+  d = int(torch.as_tensor(any_x).shape[1])
+  raw0, mask, scalar_ls = params_utils.pack_raw(params.model, d, mid == 1,
+                                                warp_func)
+  trainer = AdamTrainer(eng, kid, mid, raw0, mask, d,
+                        params.config["learning_rate"], allreduce=world > 1,
+                        tie_lengthscale=scalar_ls and d > 1)
+  model_template = dict(params.model)
+
+  def to_model(vec):
+    return params_utils.unpack_like(model_template, vec, d, mid == 1)
+
+  ds = static_ds
+  ran = False
+  for i in range(max_training_step):
+    if needs_subsample:
+      ds = pack(next(dataset_iter))
+    trainer.step(ds, use_graph=not needs_subsample)
+    ran = True
+    current_loss = trainer.loss()
+    if math.isnan(current_loss) and i == 0:
+      raise ValueError("Encountered NaN in loss function. current_loss = "
+                       f"{current_loss}.")
+    if not math.isfinite(current_loss):
+      logging.info(msg=f"{method} stopped at step {i} due to instability.")
+      break
+    if callback:
+      callback(i, to_model(trainer.accepted), current_loss)
+  if ran:
+    final = trainer.accepted
+    if not trainer.stopped:
+      # gp.py:147-150: evaluate the last update once more, accept iff finite
+      sums = eng.nll_grad(kid, mid, ds, trainer.raw, mask)
+      if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+      if math.isfinite(float(sums[0] / sums[-1])):
+        final = trainer.raw
+    params.model = to_model(final)
+  params.cache = {}
+  return params
+
+
+def sample_from_gp(key, mean_func, cov_func, params, x, warp_func=None,
+                   num_samples=1, method="cholesky", eps=1e-6):
+  """Sample functions from a GP at x (gp.py:198-239): mean + chol(K+noise+eps) z."""
+  del method
+  n = torch.as_tensor(x).shape[0]
+  _, cov = linalg.compute_delta_y_and_cov(
+      mean_func, cov_func, params, x, torch.zeros((n, 1)), warp_func, eps)
+  gen = key if isinstance(key, torch.Generator) else torch.Generator().manual_seed(
+      int(key) if key is not None else 0)
+  z = torch.randn((cov.shape[0], num_samples), generator=gen,
+                  dtype=torch.float64).to(cov.device)
+  mean = mean_func(params, x, warp_func=warp_func).to(cov.device)
+  return mean + torch.linalg.cholesky(cov) @ z
+
+
+def predict(mean_func,
+            cov_func,
+            params,
+            x_observed,
+            y_observed,
+            x_query,
+            warp_func=None,
+            full_cov=False,
+            cache=None,
+            _noise_flag=0.0,
+            _var_scale=1.0):
+  """Predict the GP at x_query conditioned on observations (gp.py:242-305).
+
+  Returns (mu (nq,1), var (nq,1)) or (mu, cov (nq,nq)) if full_cov.
+  """
+  kid = _kernel.kernel_id_of(cov_func)
+  mid = _mean.mean_id_of(mean_func)
+  eng = _engine.Engine.get()
+  x_query = eng.tensor(x_query)
+  d = x_query.shape[1]
+  raw, mask, _ = params_utils.pack_raw(params.model, d, mid == 1, warp_func)
+  if x_observed is None or torch.as_tensor(x_observed).shape[0] == 0:
+    # prior (gp.py:275-282)
+    if full_cov:
+      mu = mean_func(params, x_query, warp_func=warp_func).to(eng.device)
+      return mu, cov_func(params, x_query, warp_func=warp_func)
+    mu, var, _ = eng.predict(kid, mid, None, None, raw, mask, x_query,
+                             noise_flag=_noise_flag, var_scale=_var_scale)
+    return mu, var
+  x_observed = eng.tensor(x_observed)
+  packed = getattr(cache, "packed", None) if cache is not None else None
+  if packed is None:
+    chol, kinvy, _, packed = linalg.solve_gp_linear_system(
+        mean_func, cov_func, params, x_observed, y_observed, warp_func,
+        return_cache=True)
+  else:
+    chol, kinvy = cache.chol, cache.kinvy
+  if not full_cov:
+    mu, var, _ = eng.predict(kid, mid, x_observed, packed, raw, mask, x_query,
+                             noise_flag=_noise_flag, var_scale=_var_scale)
+    return mu, var
+  # full covariance (gp.py:295-300): off the hot path, library triangular solve
+  cov = cov_func(params, x_observed, x_query, warp_func=warp_func)
+  mu = cov.T @ kinvy + mean_func(params, x_query, warp_func=warp_func).to(
+      eng.device)
+  v = torch.linalg.solve_triangular(chol, cov, upper=False)
+  return mu, cov_func(params, x_query, warp_func=warp_func) - v.T @ v
+
+
+class GP:
+  """A Gaussian process that supports learning with historical data
+  (gp.py:308-620).  Same attributes and method semantics as the reference."""
+  dataset: Dict[Union[int, str], SubDataset]
+
+  def __init__(self, dataset, mean_func, cov_func, params, warp_func=None):
+    self.mean_func = mean_func
+    self.cov_func = cov_func
+    self.params = params if params is not None else GPParams()
+    self.warp_func = warp_func
+    self.set_dataset(dataset)
+    if "objective" not in self.params.config:
+      self.params.config["objective"] = obj.neg_log_marginal_likelihood
+    self.rng = None
+
+  # ---- dataset / cache bookkeeping (gp.py:328-346,403-452,535-538) --------
+  @staticmethod
+  def _arr(a):
+    t = torch.as_tensor(a)
+    if t.dtype != torch.float64:
+      t = t.to(torch.float64)
+    if torch.cuda.is_available() and not t.is_cuda:
+      t = t.cuda()
+    return t
+
+  def initialize_params(self, key):
+    """Initialize params (gp.py:347-401): a float lengthscale is broadcast to
+    ones(d) * l -- that is how ARD is switched on."""
+    if not self.dataset:
+      raise ValueError("Cannot initialize GPParams without dataset.")
+    if isinstance(self.params.config["objective"], str):
+      self.params.config["objective"] = getattr(
+          obj, self.params.config["objective"])
+    name = getattr(self.mean_func, "__name__", "") + getattr(
+        self.cov_func, "__name__", "")
+    if "mlp" in name or "linear" in name:
+      raise NotImplementedError("MLP / linear bases are outside the hot path")
+    ls = self.params.model.get("lengthscale", None)
+    if isinstance(ls, float):
+      self.params.model["lengthscale"] = np.ones(self.input_dim) * ls
+    self.rng = key
+
+  def set_dataset(self, dataset):
+    """Reset GP dataset (gp.py:403-419)."""
+    self.dataset = {}
+    self.params.cache = {}
+    if isinstance(dataset, list):
+      dataset = {i: dataset[i] for i in range(len(dataset))}
+    for key, val in dataset.items():
+      val = SubDataset(*val)
+      self.dataset[key] = SubDataset(self._arr(val.x), self._arr(val.y),
+                                     val.aligned)
+
+  @property
+  def input_dim(self) -> int:
+    key = list(self.dataset.keys())[0]
+    return self.dataset[key].x.shape[1]
+
+  def update_sub_dataset(self, sub_dataset, sub_dataset_key=0, is_append=False):
+    """Update a sub-dataset (gp.py:426-452)."""
+    sub_dataset = SubDataset(*sub_dataset)
+    x = self._arr(sub_dataset.x)
+    y = self._arr(sub_dataset.y)
+    if is_append:
+      if sub_dataset_key not in self.dataset:
+        assert self.dataset, "dataset cannot be empty."
+        any_x = next(iter(self.dataset.values())).x
+        self.dataset[sub_dataset_key] = SubDataset(
+            x=torch.empty((0, self.input_dim), dtype=torch.float64,
+                          device=any_x.device),
+            y=torch.empty((0, 1), dtype=torch.float64, device=any_x.device))
+      cur = self.dataset[sub_dataset_key]
+      new_x = torch.vstack((cur.x, x.reshape(-1, cur.x.shape[1]).to(cur.x.device)))
+      new_y = torch.vstack((cur.y, y.reshape(-1, cur.y.shape[1]).to(cur.y.device)))
+      self.dataset[sub_dataset_key] = SubDataset(x=new_x, y=new_y)
+    else:
+      self.dataset[sub_dataset_key] = SubDataset(x, y, sub_dataset.aligned)
+    if sub_dataset_key in self.params.cache:
+      self.params.cache[sub_dataset_key].needs_update = True
+
+  def update_model_params(self, model_params: Dict[str, Any]):
+    """Update params.model (must clean up params.cache) (gp.py:535-538)."""
+    self.params.model = model_params
+    self.params.cache = {}
+
+  # ---- training (gp.py:454-485) ------------------------------------------
+  def train(self, key=None, get_params_path=None, callback=None) -> GPParams:
+    if key is None:
+      if self.rng is None:
+        self.rng = 0
+        logging.info("Using default random state in GP.train.")
+      subkey = (int(self.rng) if not isinstance(self.rng, torch.Generator)
+                else self.rng)
+      if not isinstance(self.rng, torch.Generator):
+        self.rng = int(self.rng) + 1
+    else:
+      subkey = key
+    self.params = infer_parameters(
+        mean_func=self.mean_func,
+        cov_func=self.cov_func,
+        init_params=self.params,
+        dataset=self.dataset,
+        warp_func=self.warp_func,
+        objective=self.params.config["objective"],
+        key=subkey,
+        get_params_path=get_params_path,
+        callback=callback)
+    logging.info(msg=f"params = {self.params}")
+    return self.params
+
+  def neg_log_marginal_likelihood(self):
+    """Total nll and dict key -> nll (gp.py:487-497).  The reference evaluates
+    this with its SVD branch; the engine uses the Cholesky branch, which the
+    reference's own test pins to agree (objectives_test.py:298-301)."""
+    return obj.neg_log_marginal_likelihood(
+        mean_func=self.mean_func,
+        cov_func=self.cov_func,
+        params=self.params,
+        dataset=self.dataset,
+        warp_func=self.warp_func,
+        return_key2nll=True,
+        use_cholesky=True)
+
+  def stats(self, verbose=True):
+    raise NotImplementedError(
+        "GP.stats() needs the EKL / Euclidean objectives (gp.py:511-533), a "
+        "'next' row of the scope table; use neg_log_marginal_likelihood()")
+
+  # ---- prediction (gp.py:540-620) ----------------------------------------
+  def setup_predictor(self, sub_dataset_key=0):
+    """Compute and cache (chol, kinvy) for a sub-dataset (gp.py:540-560)."""
+    if sub_dataset_key in self.params.cache and not self.params.cache[
+        sub_dataset_key].needs_update:
+      return
+    chol, kinvy, _, packed = linalg.solve_gp_linear_system(
+        mean_func=self.mean_func,
+        cov_func=self.cov_func,
+        params=self.params,
+        x=self.dataset[sub_dataset_key].x,
+        y=self.dataset[sub_dataset_key].y,
+        warp_func=self.warp_func,
+        return_cache=True)
+    self.params.cache[sub_dataset_key] = GPCache(
+        chol=chol, kinvy=kinvy, needs_update=False, packed=packed)
+
+  def _noise_and_scale(self, with_noise, unbiased):
+    noise_flag = 1.0 if with_noise else 0.0
+    scale = 1.0
+    if unbiased:
+      len_dataset = len(
+          [k for k, v in self.dataset.items() if v.aligned is None])
+      if len_dataset > 1:
+        scale = len_dataset / (len_dataset - 1.0)
+    return noise_flag, scale
+
+  def predict(self, queried_inputs, sub_dataset_key=0, full_cov=False,
+              with_noise=True, unbiased=True):
+    """Predict mean and (co)variance at queried_inputs (gp.py:562-620): noise
+    is added WITHOUT the 1e-6 jitter, then the N/(N-1) inflation."""
+    noise_flag, scale = self._noise_and_scale(with_noise, unbiased)
+    has_obs = (sub_dataset_key in self.dataset and
+               self.dataset[sub_dataset_key].x.shape[0] > 0)
+    if sub_dataset_key in self.dataset:
+      if has_obs:
+        self.setup_predictor(sub_dataset_key)
+      x_obs = self.dataset[sub_dataset_key].x
+      y_obs = self.dataset[sub_dataset_key].y
+      cache = self.params.cache.get(sub_dataset_key) if has_obs else None
+    else:
+      x_obs = y_obs = cache = None
+    if not full_cov:
+      return predict(self.mean_func, self.cov_func, self.params, x_obs, y_obs,
+                     queried_inputs, self.warp_func, False, cache,
+                     _noise_flag=noise_flag, _var_scale=scale)
+    mu, cov = predict(self.mean_func, self.cov_func, self.params, x_obs, y_obs,
+                      queried_inputs, self.warp_func, True, cache)
+    if with_noise:
+      noise_variance, = retrieve_params(self.params, ["noise_variance"],
+                                        warp_func=self.warp_func)
+      nv = float(torch.as_tensor(noise_variance).reshape(-1)[0])
+      cov = cov + torch.eye(cov.shape[0], device=cov.device,
+                            dtype=cov.dtype) * nv
+    return mu, cov * scale
+
+  def acquisition(self, queried_inputs, sub_dataset_key, acq_id, acq_param):
+    """Fused predict + acfun_sub epilogue (acfun.py:84-88 + :96-142) with the
+    GP.predict conventions full_cov=False, with_noise=True, unbiased=True."""
+    noise_flag, scale = self._noise_and_scale(True, True)
+    kid = _kernel.kernel_id_of(self.cov_func)
+    mid = _mean.mean_id_of(self.mean_func)
+    eng = _engine.Engine.get()
+    xq = eng.tensor(queried_inputs)
+    raw, mask, _ = params_utils.pack_raw(self.params.model, xq.shape[1],
+                                         mid == 1, self.warp_func)
+    has_obs = (sub_dataset_key in self.dataset and
+               self.dataset[sub_dataset_key].x.shape[0] > 0)
+    if has_obs:
+      self.setup_predictor(sub_dataset_key)
+      x_obs = self.dataset[sub_dataset_key].x
+      packed = self.params.cache[sub_dataset_key].packed
+    else:
+      x_obs, packed = None, None
+    _, _, acq = eng.predict(kid, mid, x_obs, packed, raw, mask, xq,
+                            noise_flag=noise_flag, var_scale=scale,
+                            acq_id=acq_id, acq_param=acq_param, want_mu=False,
+                            want_var=False)
+    return acq
+
+
+class HGP(GP):
+  """Hierarchical GP over hyperparameter samples (gp.py:623-682)."""
+
+  def get_model_params_samples(self):
+    return self.params.samples if self.params.samples else [self.params.model]
+
+  def predict(self, queried_inputs, sub_dataset_key=0, full_cov=False,
+              with_noise=True):
+    results = []
+    for model_params in self.get_model_params_samples():
+      self.update_model_params(model_params)
+      results.append(super().predict(
+          queried_inputs=queried_inputs, sub_dataset_key=sub_dataset_key,
+          full_cov=full_cov, with_noise=with_noise))
+    return results

@@ -128,10 +128,14 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
  *   [3] number of accepted steps.
  * Semantics of gp.py:135-146: loss = sums[0]/sums[1+P]; if finite:
  * accepted <- raw, then raw <- raw - lr*mhat/(sqrt(vhat)+eps); else stopped=1
- * and nothing changes any more (the host loop `break`s). */
+ * and nothing changes any more (the host loop `break`s).
+ * tie_lengthscale != 0: the model has ONE scalar lengthscale broadcast over the
+ * d inputs (kernel.py:80): its gradient is the sum over k and all d entries of
+ * raw move together. */
 int hb_adam_step(hb_handle_t h, int P, void* raw, void* m, void* v,
                  void* accepted, const void* sums, void* scalars_io, double lr,
-                 double b1, double b2, double eps, void* stream);
+                 double b1, double b2, double eps, int tie_lengthscale,
+                 void* stream);
 
 /* ---- a12/a13: predictor cache, predict, acquisition --------------------- */
 /* Bytes of the opaque predictor cache for n observations (packed L^{-1} tiles,

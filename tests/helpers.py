@@ -1,0 +1,51 @@
+"""Shared helpers for the parity tests (oracle is imported HERE only)."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases():
+  return sorted(os.path.basename(p)[:-4]
+                for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+  z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+  g = {k: z[k] for k in z.files}
+  g["cov"], g["mean"] = str(g["cov"]), str(g["mean"])
+  g["d"] = int(g["d"])
+  g["ns"] = [int(n) for n in g["ns"]]
+  g["dataset"] = {t: (g[f"x{t}"], g[f"y{t}"]) for t in range(len(g["ns"]))}
+  return g
+
+
+def model_from_raw(raw, d, mean):
+  m = {"signal_variance": float(raw[1]), "noise_variance": float(raw[2]),
+       "lengthscale": np.array(raw[3:3 + d])}
+  if mean == "constant":
+    m["constant"] = float(raw[0])
+  return m
+
+
+def raw_vec(model, d):
+  ls = np.broadcast_to(np.asarray(model["lengthscale"], dtype=np.float64), (d,))
+  return np.concatenate([[model.get("constant", 0.0), model["signal_variance"],
+                          model["noise_variance"]], ls])
+
+
+def grad_vec(g, d):
+  ls = np.broadcast_to(np.asarray(g["lengthscale"], dtype=np.float64), (d,))
+  return np.concatenate([[g.get("constant", 0.0), g["signal_variance"],
+                          g["noise_variance"]], ls])
+
+
+def default_mask(d, mean="constant"):
+  return 0b110 | (((1 << d) - 1) << 3)
+
+
+def rel(a, b):
+  a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+  return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))

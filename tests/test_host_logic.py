@@ -1,0 +1,182 @@
+"""Host-side logic and the C-ABI boundary, no GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from hyperbo_b200.basics import data_utils
+from hyperbo_b200.basics import definitions as defs
+from hyperbo_b200.basics import params_utils
+from hyperbo_b200.bo_utils import const
+from hyperbo_b200.gp_utils import gp, kernel, mean, objectives, utils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+  import __graft_entry__ as ge
+  ge.build()
+  hdr = open(os.path.join(ROOT, "include", "hyperbo_b200.h")).read()
+  names = sorted(set(re.findall(r"\b(hb_[a-z_]+)\s*\(", hdr)))
+  assert len(names) >= 12, names
+  lib = ctypes.CDLL(os.path.join(ROOT, "hyperbo_b200", "libhyperbo_b200.so"))
+  for n in names:
+    assert hasattr(lib, n), f"{n} declared in include/ but not exported"
+  lib.hb_version.restype = ctypes.c_char_p
+  assert b"sm_100a" in lib.hb_version()
+
+
+def test_cabi_rejects_misuse_without_touching_a_gpu():
+  lib = ctypes.CDLL(os.path.join(ROOT, "hyperbo_b200", "libhyperbo_b200.so"))
+  assert lib.hb_create(None, 0, 0) == 1  # HB_ERR_BAD_ARG
+  h = ctypes.c_void_p()
+  rc = lib.hb_create(ctypes.byref(h), 0, 7)
+  assert rc == 1
+  assert lib.hb_destroy(None) == 1
+  lib.hb_predictor_bytes.restype = ctypes.c_int64
+  lib.hb_predictor_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+  # 130 points -> 3 blocks -> 6 tiles of 32 KiB + 3*64 alpha + header pad
+  assert lib.hb_predictor_bytes(None, 130) == (6 * 4096 + 192) * 8 + 256
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback():
+  from hyperbo_b200 import engine
+  with pytest.raises(RuntimeError, match="CUDA"):
+    engine.Engine.get()
+  params = defs.GPParams(model={"lengthscale": 1.0, "signal_variance": 1.0})
+  with pytest.raises(RuntimeError, match="CUDA"):
+    kernel.squared_exponential(params, np.zeros((3, 2)))
+
+
+def test_retrieve_params_and_missing_key():  # params_utils.py:90-111
+  p = defs.GPParams(model={"lengthscale": torch.tensor(0.0), "constant": 2.0})
+  ls, c = params_utils.retrieve_params(p, ["lengthscale", "constant"],
+                                       utils.DEFAULT_WARP_FUNC)
+  assert abs(float(ls) - (np.log(2.0) + 1e-10)) < 1e-15 and c == 2.0
+  ls, = params_utils.retrieve_params(p, ["lengthscale"], None)
+  assert float(ls) == 0.0
+  with pytest.raises(ValueError, match="Expected parameters"):
+    params_utils.retrieve_params(p, ["noise_variance"])
+
+
+def test_pack_raw_layout_mask_and_unpack():
+  model = {"constant": 5.1, "lengthscale": np.array([0.1, 0.2, 0.3]),
+           "signal_variance": 0.5, "noise_variance": -4.0}
+  raw, mask, scalar = params_utils.pack_raw(model, 3, True,
+                                            utils.DEFAULT_WARP_FUNC)
+  assert np.allclose(raw, [5.1, 0.5, -4.0, 0.1, 0.2, 0.3]) and not scalar
+  assert mask == 0b111110  # constant identity, the rest softplus+eps
+  _, mask0, _ = params_utils.pack_raw(model, 3, True, None)
+  assert mask0 == 0
+  back = params_utils.unpack_like(model, raw, 3, True)
+  assert back["constant"] == 5.1 and np.allclose(back["lengthscale"],
+                                                 model["lengthscale"])
+  # scalar lengthscale: broadcast in, summed gradient out (kernel.py:80)
+  m2 = dict(model, lengthscale=0.7)
+  raw2, _, scalar2 = params_utils.pack_raw(m2, 3, True, None)
+  assert scalar2 and np.allclose(raw2[3:], 0.7)
+  g = params_utils.unpack_like(m2, np.array([1., 2., 3., 4., 5., 6.]), 3, True,
+                               is_grad=True)
+  assert g["lengthscale"] == 15.0
+  with pytest.raises(ValueError):
+    params_utils.pack_raw(dict(model, lengthscale=np.ones(2)), 3, True, None)
+
+
+def test_unknown_warp_is_rejected():
+  wf = dict(utils.DEFAULT_WARP_FUNC, lengthscale=lambda x: x * x)
+  with pytest.raises(NotImplementedError, match="warp"):
+    params_utils.pack_raw({"lengthscale": 1.0, "signal_variance": 1.0,
+                           "noise_variance": 1.0}, 2, False, wf)
+
+
+def test_registries_keep_reference_names():  # const.py:22-50
+  assert set(const.KERNEL) == {"squared_exponential", "matern32", "matern52",
+                               "dot_product", "dot_product_mlp"}
+  assert set(const.MEAN) == {"constant", "linear", "linear_mlp", "zero"}
+  assert set(const.ACFUN) == {"expected_improvement",
+                              "probability_of_improvement", "ucb3",
+                              "random_search", "ucb2", "ucb"}
+  assert kernel.matern52.__name__ == "matern52"
+  assert "mlp" in kernel.squared_exponential_mlp.__name__
+  assert const.ACFUN["random_search"].__name__ in ("rand", "random_search")
+  p = defs.GPParams(model={})
+  for f in (kernel.dot_product, kernel.squared_exponential_mlp):
+    with pytest.raises(NotImplementedError):
+      f(p, np.zeros((2, 2)))
+  with pytest.raises(NotImplementedError):
+    mean.linear_mlp(p, np.zeros((2, 2)))
+  with pytest.raises(NotImplementedError):
+    objectives.ekl(None, None, None, None)
+
+
+def test_sub_sample_dataset_iterator():  # data_utils.py:72-100
+  ds = {
+      "a": defs.SubDataset(torch.arange(20.).reshape(10, 2), torch.arange(10.).reshape(10, 1)),
+      "b": defs.SubDataset(torch.zeros(3, 2), torch.zeros(3, 1), aligned="tag"),
+  }
+  it = data_utils.sub_sample_dataset_iterator(0, ds, 4)
+  b1, b2 = next(it), next(it)
+  assert b1["a"].x.shape == (4, 2) and b1["a"].y.shape == (4, 1)
+  # rows stay paired
+  assert torch.equal(b1["a"].x[:, 0] / 2, b1["a"].y[:, 0])
+  assert not torch.equal(b1["a"].y, b2["a"].y)
+  assert b1["b"].x.shape == (3, 2) and b1["b"].aligned == 1  # str tag -> index
+
+
+def test_gp_dataset_and_cache_bookkeeping():  # gp_test.py:209-277
+  x = torch.rand(5, 2, dtype=torch.float64)
+  y = torch.rand(5, 1, dtype=torch.float64)
+  params = defs.GPParams(model={"constant": 5., "lengthscale": 1.,
+                                "signal_variance": 1., "noise_variance": .01})
+  model = gp.GP(dataset=[(x, y), (x, y)], mean_func=mean.constant,
+                cov_func=kernel.squared_exponential, params=params)
+  assert list(model.dataset.keys()) == [0, 1] and model.input_dim == 2
+  assert model.params.config["objective"] is objectives.neg_log_marginal_likelihood
+  model.params.cache[0] = defs.GPCache(chol=None, kinvy=None, needs_update=False)
+  model.update_sub_dataset((x[:2], y[:2]), sub_dataset_key=0, is_append=True)
+  assert model.dataset[0].x.shape == (7, 2)
+  assert model.params.cache[0].needs_update is True
+  model.update_sub_dataset((x[:2], y[:2]), sub_dataset_key=0, is_append=False)
+  assert model.dataset[0].x.shape == (2, 2)
+  model.update_sub_dataset((x[:1], y[:1]), sub_dataset_key="new", is_append=True)
+  assert model.dataset["new"].x.shape == (1, 2)
+  # a single point given as 1-D arrays is appended as one row (bayesopt.py:187-190)
+  model.update_sub_dataset((x[0], y[0]), sub_dataset_key="new", is_append=True)
+  assert model.dataset["new"].x.shape == (2, 2)
+  model.update_model_params(dict(params.model))
+  assert model.params.cache == {}
+  model.set_dataset({"k": (x, y)})
+  assert list(model.dataset) == ["k"] and model.params.cache == {}
+  model.initialize_params(0)
+  assert np.allclose(model.params.model["lengthscale"], np.ones(2))  # gp.py:395-400
+
+
+def test_infer_parameters_guards():
+  params = defs.GPParams(
+      model={"constant": 0., "lengthscale": 0., "signal_variance": 0.,
+             "noise_variance": 0.},
+      config={"method": "adam", "batch_size": 10, "max_training_step": 0,
+              "learning_rate": 1e-3})
+  x, y = torch.rand(4, 1), torch.rand(4, 1)
+  # max_training_step <= 0 -> unchanged (gp.py:111-112); empty dataset too
+  assert gp.infer_parameters(mean.constant, kernel.matern32, params,
+                             {0: (x, y)}) is params
+  assert gp.infer_parameters(mean.constant, kernel.matern32, params, {}) is params
+  params.config["max_training_step"] = 1
+  params.config["method"] = "lbfgs"
+  with pytest.raises(NotImplementedError):
+    gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)})
+  params.config["method"] = "nope"
+  with pytest.raises(ValueError):
+    gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)})
+
+
+def test_shard_tasks_round_robin():
+  items = list(range(10))
+  shards = [gp.shard_tasks(items, r, 4) for r in range(4)]
+  assert sorted(sum(shards, [])) == items
+  assert shards[1] == [1, 5, 9]

@@ -1,0 +1,193 @@
+"""Pins the CPU oracle (not gpu): golden fixtures, the reference's own test
+identities, closed-form known answers, finite differences, and
+agreement of the two independent restatements."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import hyperbo_oracle as O
+from oracle import hyperbo_oracle_torch as OT
+from tests import helpers as H
+
+WF = O.DEFAULT_WARP_FUNC
+
+
+@pytest.mark.parametrize("name", H.golden_cases())
+def test_oracle_matches_golden(name):
+  g = H.load_golden(name)
+  model = H.model_from_raw(g["raw"], g["d"], g["mean"])
+  val, grad = O.nll_value_and_grad(g["mean"], g["cov"], model, g["dataset"], WF)
+  assert abs(val - g["mean_nll"]) <= 1e-12 * abs(g["mean_nll"])
+  assert H.rel(H.grad_vec(grad, g["d"]), g["grad"]) < 1e-10
+  mu, var = O.gp_predict(g["mean"], g["cov"], model, g["dataset"], g["xq"], 0, WF)
+  assert H.rel(mu.ravel(), g["mu"]) < 1e-12
+  assert H.rel(var.ravel(), g["var"]) < 1e-10
+
+
+@pytest.mark.parametrize("cov", O.KERNELS)
+def test_two_oracles_agree_incl_duplicate_points(cov):
+  ds = O.make_dataset(3, 40, 3, cov)
+  x, y = ds[0]
+  x[5] = x[7]  # r = 0 off the diagonal: exercises _safe_sqrt (linalg.py:175-197)
+  ds[0] = (x, y)
+  model = O.init_raw_params(3)
+  model["lengthscale"] = np.array([0.1, -0.3, 0.5])
+  v, g = O.nll_value_and_grad("constant", cov, model, ds, WF)
+  vt, gt = OT.value_and_grad("constant", cov, model, ds)
+  assert abs(v - vt) < 1e-12 * abs(v)
+  for k in g:
+    assert H.rel(g[k], gt[k]) < 1e-11, k
+
+
+def test_scalar_lengthscale_gradient_is_summed():
+  model = {"constant": 5.1, "lengthscale": 0.2, "signal_variance": 0.0,
+           "noise_variance": -4.0}
+  ds = O.make_dataset(2, 30, 4)
+  v, g = O.nll_value_and_grad("constant", "matern52", model, ds, WF)
+  vt, gt = OT.value_and_grad("constant", "matern52", model, ds)
+  assert abs(v - vt) < 1e-12 * abs(v)
+  assert abs(float(g["lengthscale"]) - float(gt["lengthscale"])) < 1e-10
+
+
+@pytest.mark.parametrize("cov", O.KERNELS)
+def test_finite_differences(cov):
+  ds = O.make_dataset(2, 25, 2, cov)
+  model = O.init_raw_params(2)
+  _, g = O.nll_value_and_grad("constant", cov, model, ds, WF)
+  h = 1e-6
+  for key in ("constant", "signal_variance", "noise_variance"):
+    mp, mm = dict(model), dict(model)
+    mp[key] = model[key] + h
+    mm[key] = model[key] - h
+    fd = (O.neg_log_marginal_likelihood("constant", cov, mp, ds, WF) -
+          O.neg_log_marginal_likelihood("constant", cov, mm, ds, WF)) / (2 * h)
+    assert abs(fd - g[key]) < 1e-6 * max(1.0, abs(fd))
+  for k in range(2):
+    mp, mm = dict(model), dict(model)
+    e = np.zeros(2)
+    e[k] = h
+    mp["lengthscale"] = model["lengthscale"] + e
+    mm["lengthscale"] = model["lengthscale"] - e
+    fd = (O.neg_log_marginal_likelihood("constant", cov, mp, ds, WF) -
+          O.neg_log_marginal_likelihood("constant", cov, mm, ds, WF)) / (2 * h)
+    assert abs(fd - g["lengthscale"][k]) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_known_answer_n1_and_n2():
+  # n = 1: nll = .5 (y-c)^2 / v + .5 log v + .5 log 2pi, v = sf2 + sn2 + 1e-6
+  model = {"constant": 0.3, "lengthscale": 0.7, "signal_variance": 1.3,
+           "noise_variance": 0.2}
+  x, y = np.array([[0.4]]), np.array([[1.1]])
+  v = 1.3 + 0.2 + 1e-6
+  want = 0.5 * (1.1 - 0.3)**2 / v + 0.5 * math.log(v) + 0.5 * math.log(2 * math.pi)
+  got = O.nll_sub_dataset("constant", "squared_exponential", model, x, y)
+  assert abs(got - want) < 1e-14
+  # n = 2 closed form
+  x = np.array([[0.0], [0.5]])
+  y = np.array([[1.0], [-0.5]])
+  k = 1.3 * math.exp(-0.5 * (0.5 / 0.7)**2)
+  a = v
+  det = a * a - k * k
+  r = y.ravel() - 0.3
+  quad = (a * r[0]**2 - 2 * k * r[0] * r[1] + a * r[1]**2) / det
+  want = 0.5 * quad + 0.5 * math.log(det) + math.log(2 * math.pi)
+  got = O.nll_sub_dataset("constant", "squared_exponential", model, x, y)
+  assert abs(got - want) < 1e-13
+
+
+@pytest.mark.parametrize("cov", O.KERNELS)
+def test_gram_shape_symmetry_psd(cov):  # kernel_test.py:77-152
+  rng = np.random.default_rng(0)
+  x1, x2 = rng.normal(size=(30, 3)), rng.normal(size=(20, 3))
+  model = {"lengthscale": np.array([0.5, 1.0, 2.0]), "signal_variance": 1.7}
+  k12 = O.cov_matrix(cov, model, x1, x2)
+  assert k12.shape == (30, 20)
+  k11 = O.cov_matrix(cov, model, x1)
+  assert np.allclose(k11, k11.T, atol=1e-12)
+  assert np.linalg.eigvalsh(k11).min() > -1e-10
+  assert np.allclose(np.diag(k11), 1.7)
+  assert O.cov_matrix(cov, model, x1, diag=True).shape == (30,)
+  # diag is ignored when vx2 is given (kernel.py:54-58)
+  assert O.cov_matrix(cov, model, x1, x2, diag=True).shape == (30, 20)
+
+
+def test_predict_identities():  # gp_test.py:150-207
+  x, y = O.make_task(3, 20, 1)
+  xq = np.random.default_rng(1).normal(size=(10, 1))
+  model = dict(O.GROUND_TRUTH)
+  mu, var = O.predict("constant", "squared_exponential", model, x, y, xq)
+  mu_m, var_m = O.gp_predict("constant", "squared_exponential", model,
+                             {0: (x, y)}, xq, 0, with_noise=True)
+  assert mu.shape == (10, 1) and var.shape == (10, 1)
+  assert np.allclose(mu, mu_m, atol=1e-12)
+  assert np.allclose(var + model["noise_variance"], var_m, atol=1e-12)
+  mu2, cov = O.predict("constant", "squared_exponential", model, x, y, xq,
+                       full_cov=True)
+  assert cov.shape == (10, 10)
+  assert np.allclose(np.diag(cov), var.ravel(), atol=1e-9)
+  # prior branch with no observations (gp.py:275-282)
+  mu0, var0 = O.predict("constant", "squared_exponential", model, None, None, xq)
+  assert np.allclose(mu0, 5.0) and np.allclose(var0, 1.0)
+
+
+def test_svd_nll_matches_cholesky_nll():  # objectives_test.py:298-301
+  ds = O.make_dataset(3, 20, 2)
+  model = O.init_raw_params(2)
+  a = O.neg_log_marginal_likelihood("constant", "squared_exponential", model, ds,
+                                    WF, use_cholesky=True)
+  b = O.neg_log_marginal_likelihood("constant", "squared_exponential", model, ds,
+                                    WF, use_cholesky=False)
+  assert abs(a / b - 1) < 1e-8
+
+
+def test_unbiased_inflation_and_noise_without_jitter():  # gp.py:607-619
+  ds = O.make_dataset(3, 15, 2)
+  xq = np.random.default_rng(2).random((5, 2))
+  model = O.init_raw_params(2)
+  _, v1 = O.gp_predict("constant", "squared_exponential", model, ds, xq, 0, WF,
+                       with_noise=False, unbiased=False)
+  _, v2 = O.gp_predict("constant", "squared_exponential", model, ds, xq, 0, WF,
+                       with_noise=True, unbiased=True)
+  nv = float(O.default_softplus(model["noise_variance"]))
+  assert np.allclose(v2, (v1 + nv) * 1.5, rtol=1e-12)
+
+
+def test_training_decreases_nll_and_adam_matches_torch():  # gp_test.py:148
+  ds = O.make_dataset(4, 30, 1)
+  model = O.init_raw_params(1)
+  init = O.neg_log_marginal_likelihood("constant", "squared_exponential", model,
+                                       ds, WF)
+  out, losses = O.infer_parameters_adam("constant", "squared_exponential", model,
+                                        ds, WF, 1e-2, 5, 100)
+  final = O.neg_log_marginal_likelihood("constant", "squared_exponential", out,
+                                        ds, WF)
+  assert final < init and len(losses) == 5
+  x = np.stack([ds[t][0] for t in range(4)])
+  y = np.stack([ds[t][1] for t in range(4)])
+  tr = OT.AdamTrainer("constant", "squared_exponential", model, x, y, lr=1e-2)
+  tl = [tr.step() for _ in range(5)]
+  assert H.rel(tl, losses) < 1e-10
+
+
+def test_skips_empty_and_aligned_tasks():  # objectives.py:181-185
+  ds = O.make_dataset(2, 10, 1)
+  full = O.neg_log_marginal_likelihood("constant", "squared_exponential",
+                                       O.init_raw_params(1), ds, WF)
+  ds[7] = (np.zeros((0, 1)), np.zeros((0, 1)))
+  ds[8] = (ds[0][0], ds[0][1], "aligned-tag")
+  again = O.neg_log_marginal_likelihood("constant", "squared_exponential",
+                                        O.init_raw_params(1), ds, WF)
+  assert full == again
+
+
+def test_acquisition_shapes_and_values():  # acfun_test.py:43-72
+  ds = O.make_dataset(2, 12, 2)
+  xq = np.random.default_rng(3).random((9, 2))
+  for name in ("ei", "pi", "pi2", "pi3", "ucb", "ucb2", "ucb4"):
+    out = O.acquisition(name, "constant", "matern32", O.init_raw_params(2), ds,
+                        0, xq, WF)
+    assert out.shape == (9, 1) and np.all(np.isfinite(out))
+  # EI >= 0 and EI(mu=target, std) = std * pdf(0)
+  assert np.isclose(O.expected_improvement_sub(1.0, 2.0, 1.0),
+                    2.0 / math.sqrt(2 * math.pi))
