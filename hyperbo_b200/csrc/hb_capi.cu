@@ -257,7 +257,7 @@ int run_factor_k(hb_handle_t h, const Plan& p, const Params& P, cudaStream_t st)
 
 // prep + factorisation (+ M) + alpha / per-task nll
 int run_factor(hb_handle_t h, const Plan& p, const Params& P, const void* raw,
-               uint32_t warp_mask, cudaStream_t st) {
+               uint64_t warp_mask, cudaStream_t st) {
   k_prep<<<1, 64, 0, st>>>((const double*)raw, warp_mask, p.d, P.mean_id,
                            (double*)h->theta.p, P.bad, p.T);
   HB_LAUNCH_CHECK();
@@ -277,7 +277,7 @@ int run_factor(hb_handle_t h, const Plan& p, const Params& P, const void* raw,
 
 int factorize_impl(hb_handle_t h, int kernel_id, int mean_id, int T,
                    const int64_t* offs, int d, const void* X, const void* y,
-                   const void* raw, uint32_t warp_mask, int with_trtri,
+                   const void* raw, uint64_t warp_mask, int with_trtri,
                    void* chol_out, void* alpha_out, void* nll_out,
                    int32_t* info_out, cudaStream_t st, Plan** plan_out,
                    Params* P_out) {
@@ -364,7 +364,7 @@ int64_t hb_workspace_bytes(hb_handle_t h) { return h ? (int64_t)total_ws(h) : 0;
 
 int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,
                      const void* X2, int64_t n2, int d, const void* raw,
-                     uint32_t warp_mask, int diag_only, int add_noise,
+                     uint64_t warp_mask, int diag_only, int add_noise,
                      double jitter, void* out, void* stream) {
   int rc = check_common(h, kernel_id, 1, d);
   if (rc) return rc;
@@ -403,7 +403,7 @@ int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,
 
 int hb_factorize_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
                          const int64_t* offs, int d, const void* X,
-                         const void* y, const void* raw, uint32_t warp_mask,
+                         const void* y, const void* raw, uint64_t warp_mask,
                          void* chol_out, void* alpha_out, void* nll_out,
                          int32_t* info_out, void* stream) {
   Plan* p;
@@ -416,7 +416,7 @@ int hb_factorize_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
 
 int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
                         const int64_t* offs, int d, const void* X, const void* y,
-                        const void* raw, uint32_t warp_mask, void* sums_out,
+                        const void* raw, uint64_t warp_mask, void* sums_out,
                         void* nll_task_out, int32_t* info_out, void* stream) {
   int rc = check_common(h, kernel_id, mean_id, d);
   if (rc) return rc;
@@ -478,7 +478,7 @@ int64_t hb_predictor_bytes(hb_handle_t h, int64_t n) {
 
 int hb_build_predictor(hb_handle_t h, int kernel_id, int mean_id, int64_t n,
                        int d, const void* X, const void* y, const void* raw,
-                       uint32_t warp_mask, void* cache, void* chol_out,
+                       uint64_t warp_mask, void* cache, void* chol_out,
                        void* kinvy_out, void* nll_out, int32_t* info_out,
                        void* stream) {
   if (!h) return HB_ERR_BAD_ARG;
@@ -502,7 +502,7 @@ int hb_build_predictor(hb_handle_t h, int kernel_id, int mean_id, int64_t n,
 
 int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
                const void* X, const void* cache, const void* raw,
-               uint32_t warp_mask, int64_t nq, const void* Xq,
+               uint64_t warp_mask, int64_t nq, const void* Xq,
                double noise_add_flag, double var_scale, int acq_id,
                double acq_param, void* mu_out, void* var_out, void* acq_out,
                void* stream) {

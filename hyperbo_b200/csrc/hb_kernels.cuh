@@ -81,13 +81,13 @@ __device__ __forceinline__ double sigmoid(double x) {
 
 // raw -> theta (params_utils.retrieve_params + utils.DEFAULT_WARP_FUNC), the
 // chain-rule factors d theta / d raw, and per-call state reset.
-__global__ void k_prep(const double* __restrict__ raw, uint32_t warp_mask,
+__global__ void k_prep(const double* __restrict__ raw, uint64_t warp_mask,
                        int d, int mean_id, double* __restrict__ theta,
                        unsigned* bad, int T) {
   const int p = threadIdx.x;
   if (p < 3 + d) {
     const double r = raw[p];
-    const bool wp = (warp_mask >> p) & 1u;
+    const bool wp = (warp_mask >> p) & 1ull;
     double v = wp ? softplus(r) + EPS_WARP : r;
     double ch = wp ? sigmoid(r) : 1.0;
     if (p == 0 && mean_id == 0) { v = 0.0; ch = 0.0; }
@@ -691,7 +691,7 @@ __global__ void k_reduce_final(Params P, double* __restrict__ out,
     }
     v = block_sum(v, red);
     if (threadIdx.x == 0) {
-      if (q >= 1 && q <= np) {
+      if (q >= 1 && q <= np && v != 0.0) {  // (an empty batch stays exactly 0)
         const int p = q - 1;
         if (p == 1) v /= sv;                                    // <G,K>/sv
         if (p >= 3) v *= P.theta[TH_INVLS + (p - 3)];           // /l_k

@@ -55,7 +55,7 @@ PYBIND11_MODULE(_C, m) {
            [](Handle& s, int64_t n) { return hb_predictor_bytes(s.h, n); })
       .def("kernel_matrix",
            [](Handle& s, int kernel_id, ptr_t X1, int64_t n1, ptr_t X2, int64_t n2,
-              int d, ptr_t raw, uint32_t mask, int diag_only, int add_noise,
+              int d, ptr_t raw, uint64_t mask, int diag_only, int add_noise,
               double jitter, ptr_t out, ptr_t stream) {
              py::gil_scoped_release rel;
              s.check(hb_kernel_matrix(s.h, kernel_id, P(X1), n1, P(X2), n2, d,
@@ -65,7 +65,7 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("factorize_batched",
            [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
-              int d, ptr_t X, ptr_t y, ptr_t raw, uint32_t mask, ptr_t chol,
+              int d, ptr_t X, ptr_t y, ptr_t raw, uint64_t mask, ptr_t chol,
               ptr_t alpha, ptr_t nll, ptr_t info, ptr_t stream) {
              py::gil_scoped_release rel;
              s.check(hb_factorize_batched(
@@ -76,7 +76,7 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("nll_grad_batched",
            [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
-              int d, ptr_t X, ptr_t y, ptr_t raw, uint32_t mask, ptr_t sums,
+              int d, ptr_t X, ptr_t y, ptr_t raw, uint64_t mask, ptr_t sums,
               ptr_t nll_task, ptr_t info, ptr_t stream) {
              py::gil_scoped_release rel;
              s.check(hb_nll_grad_batched(
@@ -97,7 +97,7 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("build_predictor",
            [](Handle& s, int kernel_id, int mean_id, int64_t n, int d, ptr_t X,
-              ptr_t y, ptr_t raw, uint32_t mask, ptr_t cache, ptr_t chol,
+              ptr_t y, ptr_t raw, uint64_t mask, ptr_t cache, ptr_t chol,
               ptr_t kinvy, ptr_t nll, ptr_t info, ptr_t stream) {
              py::gil_scoped_release rel;
              s.check(hb_build_predictor(s.h, kernel_id, mean_id, n, d, P(X), P(y),
@@ -107,7 +107,7 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("predict",
            [](Handle& s, int kernel_id, int mean_id, int64_t n, int d, ptr_t X,
-              ptr_t cache, ptr_t raw, uint32_t mask, int64_t nq, ptr_t Xq,
+              ptr_t cache, ptr_t raw, uint64_t mask, int64_t nq, ptr_t Xq,
               double noise_flag, double var_scale, int acq_id, double acq_param,
               ptr_t mu, ptr_t var, ptr_t acq, ptr_t stream) {
              py::gil_scoped_release rel;

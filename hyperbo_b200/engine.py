@@ -85,6 +85,8 @@ class Engine:
     return torch.cuda.current_stream(self.device).cuda_stream
 
   def tensor(self, a, shape=None) -> torch.Tensor:
+    if not isinstance(a, torch.Tensor):  # python floats/lists must not round
+      a = np.asarray(a, dtype=np.float64)  # through torch's float32 default
     t = torch.as_tensor(a)
     t = t.to(device=self.device, dtype=self.dtype)
     if shape is not None:

@@ -308,6 +308,8 @@ class GP:
   # ---- dataset / cache bookkeeping (gp.py:328-346,403-452,535-538) --------
   @staticmethod
   def _arr(a):
+    if not isinstance(a, torch.Tensor):
+      a = np.asarray(a, dtype=np.float64)
     t = torch.as_tensor(a)
     if t.dtype != torch.float64:
       t = t.to(torch.float64)
@@ -469,7 +471,7 @@ class GP:
     if with_noise:
       noise_variance, = retrieve_params(self.params, ["noise_variance"],
                                         warp_func=self.warp_func)
-      nv = float(torch.as_tensor(noise_variance).reshape(-1)[0])
+      nv = float(torch.as_tensor(noise_variance, dtype=torch.float64).reshape(-1)[0])
       cov = cov + torch.eye(cov.shape[0], device=cov.device,
                             dtype=cov.dtype) * nv
     return mu, cov * scale

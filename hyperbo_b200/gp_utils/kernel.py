@@ -17,6 +17,9 @@ retrieve_params = params_utils.retrieve_params
 
 
 def _as_2d(v):
+  if not isinstance(v, torch.Tensor):
+    import numpy as np
+    v = np.asarray(v, dtype=np.float64)
   t = torch.as_tensor(v)
   if t.dim() == 1:
     t = t[None, :]

@@ -32,7 +32,7 @@ def constant(params, vx, warp_func=None):
   """Constant mean function (mean.py:60-64)."""
   val, = retrieve_params(params, ["constant"], warp_func)
   n = torch.as_tensor(vx).shape[0]
-  val = float(torch.as_tensor(val).reshape(-1)[0])
+  val = float(torch.as_tensor(val, dtype=torch.float64).reshape(-1)[0])
   return torch.full((n, 1), val, dtype=torch.float64, device=_device_of(vx))
 
 

@@ -85,7 +85,7 @@ int64_t hb_workspace_bytes(hb_handle_t h);
  * (kernel.py:54-56 -- diag is ignored when X2 is given). */
 int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,
                      const void* X2_or_null, int64_t n2, int d,
-                     const void* raw, uint32_t warp_mask, int diag_only,
+                     const void* raw, uint64_t warp_mask, int diag_only,
                      int add_noise, double jitter, void* out, void* stream);
 
 /* ---- a7-a10: batched factorisation + per-task NLL ----------------------- */
@@ -100,7 +100,7 @@ int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,
  * alpha_out_or_null: (sum n,)  nll_out_or_null: (T,)  info_out_or_null: (T,) int32. */
 int hb_factorize_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
                          const int64_t* offs_host, int d, const void* X,
-                         const void* y, const void* raw, uint32_t warp_mask,
+                         const void* y, const void* raw, uint64_t warp_mask,
                          void* chol_out_or_null, void* alpha_out_or_null,
                          void* nll_out_or_null, int32_t* info_out_or_null,
                          void* stream);
@@ -117,7 +117,7 @@ int hb_factorize_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
  * (return_key2nll, objectives.py:208-209). */
 int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
                         const int64_t* offs_host, int d, const void* X,
-                        const void* y, const void* raw, uint32_t warp_mask,
+                        const void* y, const void* raw, uint64_t warp_mask,
                         void* sums_out, void* nll_task_out_or_null,
                         int32_t* info_out_or_null, void* stream);
 
@@ -146,7 +146,7 @@ int64_t hb_predictor_bytes(hb_handle_t h, int64_t n);
  * chol (n,n) row-major lower and kinvy (n,). */
 int hb_build_predictor(hb_handle_t h, int kernel_id, int mean_id, int64_t n,
                        int d, const void* X, const void* y, const void* raw,
-                       uint32_t warp_mask, void* cache, void* chol_out_or_null,
+                       uint64_t warp_mask, void* cache, void* chol_out_or_null,
                        void* kinvy_out_or_null, void* nll_out_or_null,
                        int32_t* info_out_or_null, void* stream);
 /* gp.predict (gp_utils/gp.py:242-305, full_cov=False) + GP.predict's noise /
@@ -157,7 +157,7 @@ int hb_build_predictor(hb_handle_t h, int kernel_id, int mean_id, int64_t n,
  * Outputs (nq,) each; any of mu/var/acq may be NULL. */
 int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
                const void* X, const void* cache, const void* raw,
-               uint32_t warp_mask, int64_t nq, const void* Xq,
+               uint64_t warp_mask, int64_t nq, const void* Xq,
                double noise_add_flag, double var_scale, int acq_id,
                double acq_param, void* mu_out, void* var_out, void* acq_out,
                void* stream);

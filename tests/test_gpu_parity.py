@@ -153,25 +153,30 @@ def test_empty_tasks_are_skipped(eng):
   s2 = eng.nll_grad(kid, mid, ds0, H.raw_vec(model, 2), H.default_mask(2)).cpu().numpy()
   assert s2[-1] == 2 and np.allclose(s2, sums, rtol=1e-14)
   # no tasks at all -> zeros (objectives.py:192-193)
-  z = eng.nll_grad(kid, mid, _pack(eng, {}), H.raw_vec(model, 1), 0).cpu().numpy()
+  z = eng.nll_grad(kid, mid, _pack(eng, {}), H.raw_vec(O.init_raw_params(1), 1), 0).cpu().numpy()
   assert np.all(z == 0.0)
 
 
 def test_non_pd_sets_info_and_nan_without_raising(eng):
-  # identical points, zero noise, negative jitter-free margin: K~ is singular
-  x = np.zeros((40, 1))
-  x[:, 0] = 0.5
+  # task 0: 40 identical points with the noise cancelling the jitter -> K~ is
+  # the rank-1 all-ones matrix, breakdown at column 2.  Task 1: a well-spaced
+  # grid that stays PD without noise at this short lengthscale.
+  x = np.full((40, 1), 0.5)
   y = np.ones((40, 1))
-  model = {"constant": 0.0, "lengthscale": np.array([1.0]),
-           "signal_variance": 1.0, "noise_variance": -1e-6}  # cancels the jitter
+  x1 = np.linspace(0.0, 1.0, 20)[:, None]
+  y1 = np.sin(6 * x1)
+  model = {"constant": 0.0, "lengthscale": np.array([0.05]),
+           "signal_variance": 1.0, "noise_variance": -1e-6}
   kid, mid = _ids("squared_exponential", "constant")
-  ds = _pack(eng, {0: (x, y), 1: O.make_task(1, 20, 1)})
+  ds = _pack(eng, {0: (x, y), 1: (x1, y1)})
   _, _, nll, info = eng.factorize(kid, mid, ds, H.raw_vec(model, 1), 0,
                                   want_chol=False, want_alpha=False)
-  assert info[0].item() > 0 and np.isnan(nll[0].item())
+  assert info[0].item() == 2 and np.isnan(nll[0].item())
   assert info[1].item() == 0 and np.isfinite(nll[1].item())
+  ref = O.nll_sub_dataset("constant", "squared_exponential", model, x1, y1, None)
+  assert abs(nll[1].item() - ref) < 1e-9 * abs(ref)
   sums = eng.nll_grad(kid, mid, ds, H.raw_vec(model, 1), 0).cpu().numpy()
-  assert np.isnan(sums[0])
+  assert np.isnan(sums[0])  # the mean loss is NaN -> the host loop stops
 
 
 def test_large_n_blocked_path(eng):
