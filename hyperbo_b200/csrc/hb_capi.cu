@@ -45,6 +45,8 @@ struct hb_handle_s {
       sums, kst, mupart, vpart, pcache;
   bool attr_set = false;
   int smem_d = -1;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[HB_PROFILE_SECTIONS];
 };
 
 namespace {
@@ -241,6 +243,26 @@ Params make_params(hb_handle_t h, const Plan& p, int kernel_id, int mean_id,
     }                                                      \
   } while (0)
 
+struct Section {
+  hb_handle_t h;
+  int id;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  Section(hb_handle_t h_, int id_, cudaStream_t st_) : h(h_), id(id_), st(st_) {
+    if (!h->profiling) return;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+      e0 = e1 = nullptr;
+      return;
+    }
+    cudaEventRecord(e0, st);
+  }
+  ~Section() {
+    if (!e0) return;
+    cudaEventRecord(e1, st);
+    h->prof_ev[id].emplace_back(e0, e1);
+  }
+};
+
 template <int KID>
 int run_factor_k(hb_handle_t h, const Plan& p, const Params& P, cudaStream_t st) {
   const size_t smem = step_smem_bytes(p.d);
@@ -258,17 +280,21 @@ int run_factor_k(hb_handle_t h, const Plan& p, const Params& P, cudaStream_t st)
 // prep + factorisation (+ M) + alpha / per-task nll
 int run_factor(hb_handle_t h, const Plan& p, const Params& P, const void* raw,
                uint64_t warp_mask, cudaStream_t st) {
-  k_prep<<<1, 64, 0, st>>>((const double*)raw, warp_mask, p.d, P.mean_id,
-                           (double*)h->theta.p, P.bad, p.T);
-  HB_LAUNCH_CHECK();
-  if (p.T == 0 || p.nblk_max == 0) return HB_OK;
-  int rc;
-  switch (P.kernel_id) {
-    case 0: rc = run_factor_k<0>(h, p, P, st); break;
-    case 1: rc = run_factor_k<1>(h, p, P, st); break;
-    default: rc = run_factor_k<2>(h, p, P, st); break;
+  {
+    Section sec(h, 0, st);
+    k_prep<<<1, 64, 0, st>>>((const double*)raw, warp_mask, p.d, P.mean_id,
+                             (double*)h->theta.p, P.bad, p.T);
+    HB_LAUNCH_CHECK();
+    if (p.T == 0 || p.nblk_max == 0) return HB_OK;
+    int rc;
+    switch (P.kernel_id) {
+      case 0: rc = run_factor_k<0>(h, p, P, st); break;
+      case 1: rc = run_factor_k<1>(h, p, P, st); break;
+      default: rc = run_factor_k<2>(h, p, P, st); break;
+    }
+    if (rc) return rc;
   }
-  if (rc) return rc;
+  Section sec(h, 1, st);
   k_alpha<<<dim3(p.nblk_max, p.T), NTHREADS, 0, st>>>(P);
   HB_LAUNCH_CHECK();
   return HB_OK;
@@ -362,6 +388,35 @@ const char* hb_last_error(hb_handle_t h) { return h ? h->err.c_str() : "null han
 int64_t hb_launch_count(hb_handle_t h) { return h ? h->launches : 0; }
 int64_t hb_workspace_bytes(hb_handle_t h) { return h ? (int64_t)total_ws(h) : 0; }
 
+int hb_profile_enable(hb_handle_t h, int enable) {
+  if (!h) return HB_ERR_BAD_ARG;
+  for (auto& v : h->prof_ev) {
+    for (auto& e : v) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    v.clear();
+  }
+  h->profiling = enable != 0;
+  return HB_OK;
+}
+
+int hb_profile_read(hb_handle_t h, double* ms_out, int64_t* count_out) {
+  if (!h || !ms_out || !count_out) return HB_ERR_BAD_ARG;
+  for (int s = 0; s < HB_PROFILE_SECTIONS; ++s) {
+    double tot = 0.0;
+    for (auto& e : h->prof_ev[s]) {
+      HB_CUDA(cudaEventSynchronize(e.second));
+      float ms = 0.f;
+      HB_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+      tot += ms;
+    }
+    ms_out[s] = tot;
+    count_out[s] = (int64_t)h->prof_ev[s].size();
+  }
+  return HB_OK;
+}
+
 int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,
                      const void* X2, int64_t n2, int d, const void* raw,
                      uint64_t warp_mask, int diag_only, int add_noise,
@@ -433,17 +488,24 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
     const int nt = p->nblk_max * (p->nblk_max + 1) / 2;
     const size_t smem = lauum_smem_bytes(d);
     dim3 grid(nt, T);
-    switch (kernel_id) {
-      case 0: k_lauum_grad<0><<<grid, NTHREADS, smem, st>>>(P); break;
-      case 1: k_lauum_grad<1><<<grid, NTHREADS, smem, st>>>(P); break;
-      default: k_lauum_grad<2><<<grid, NTHREADS, smem, st>>>(P); break;
+    {
+      Section sec(h, 2, st);
+      switch (kernel_id) {
+        case 0: k_lauum_grad<0><<<grid, NTHREADS, smem, st>>>(P); break;
+        case 1: k_lauum_grad<1><<<grid, NTHREADS, smem, st>>>(P); break;
+        default: k_lauum_grad<2><<<grid, NTHREADS, smem, st>>>(P); break;
+      }
+      HB_LAUNCH_CHECK();
     }
-    HB_LAUNCH_CHECK();
+    Section sec(h, 3, st);
     k_reduce_task<<<T, 64, 0, st>>>(P);
     HB_LAUNCH_CHECK();
   }
-  k_reduce_final<<<1, 256, 0, st>>>(P, (double*)sums_out, (double*)nll_task_out);
-  HB_LAUNCH_CHECK();
+  {
+    Section sec(h, 3, st);
+    k_reduce_final<<<1, 256, 0, st>>>(P, (double*)sums_out, (double*)nll_task_out);
+    HB_LAUNCH_CHECK();
+  }
   if (info_out && T > 0) {
     k_copy_info<<<(T + 255) / 256, 256, 0, st>>>(P.info, info_out, T);
     HB_LAUNCH_CHECK();

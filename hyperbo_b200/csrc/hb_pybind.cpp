@@ -51,6 +51,18 @@ PYBIND11_MODULE(_C, m) {
       .def(py::init<int, int>(), py::arg("device"), py::arg("dtype"))
       .def("launch_count", [](Handle& s) { return hb_launch_count(s.h); })
       .def("workspace_bytes", [](Handle& s) { return hb_workspace_bytes(s.h); })
+      .def("profile_enable",
+           [](Handle& s, bool on) {
+             s.check(hb_profile_enable(s.h, on ? 1 : 0), "hb_profile_enable");
+           })
+      .def("profile_read",
+           [](Handle& s) {
+             std::vector<double> ms(HB_PROFILE_SECTIONS);
+             std::vector<int64_t> cnt(HB_PROFILE_SECTIONS);
+             s.check(hb_profile_read(s.h, ms.data(), cnt.data()),
+                     "hb_profile_read");
+             return std::make_pair(ms, cnt);
+           })
       .def("predictor_bytes",
            [](Handle& s, int64_t n) { return hb_predictor_bytes(s.h, n); })
       .def("kernel_matrix",

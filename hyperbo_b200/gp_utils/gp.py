@@ -110,6 +110,15 @@ class AdamTrainer:
       self._graph, self._graph_ds = g, ds
     self._graph.replay()
 
+  def step_from_host(self, ds, x_host: torch.Tensor, y_host: torch.Tensor):
+    """One optimiser step whose batch arrives in (pinned) HOST memory: copies
+    it into the packed device batch `ds` on the current stream, then steps.
+    This is the shape of the reference's loop, where every step receives a
+    fresh (sub-sampled) batch from the host iterator (gp.py:133)."""
+    ds.x.copy_(x_host, non_blocking=True)
+    ds.y.copy_(y_host, non_blocking=True)
+    self._enqueue(ds)
+
   def loss(self) -> float:
     return float(self.scal[0])  # device -> host sync (gp.py:135-138)
 

@@ -75,6 +75,16 @@ const char* hb_version(void);
 int64_t hb_launch_count(hb_handle_t h);
 /* Bytes of device workspace currently held. */
 int64_t hb_workspace_bytes(hb_handle_t h);
+/* Per-kernel timing for bench.py's roofline: when enabled, CUDA events are
+ * recorded on the caller's stream around each section of
+ * hb_nll_grad_batched / hb_factorize_batched:
+ *   0 = factorisation launches (k_prep + k_step x (nblk+1))
+ *   1 = k_alpha   2 = k_lauum_grad   3 = reductions
+ * hb_profile_read synchronises on the recorded events and returns the
+ * accumulated milliseconds and launch-group counts since the last enable. */
+#define HB_PROFILE_SECTIONS 4
+int hb_profile_enable(hb_handle_t h, int enable);
+int hb_profile_read(hb_handle_t h, double* ms_out, int64_t* count_out);
 
 /* ---- a4-a7: Gram / cross-Gram ------------------------------------------- */
 /* kernel.covariance_matrix.matrix_map (gp_utils/kernel.py:33-58) for
