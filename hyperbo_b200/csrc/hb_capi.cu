@@ -175,6 +175,13 @@ int set_attrs_k(hb_handle_t h, int d) {
   HB_CUDA(cudaFuncSetAttribute(k_lauum_grad<KID>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)lauum_smem_bytes(MAX_DIM)));
+  // two ~106 KiB CTAs per SM need the full shared-memory carveout
+  HB_CUDA(cudaFuncSetAttribute(k_step<KID>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared));
+  HB_CUDA(cudaFuncSetAttribute(k_lauum_grad<KID>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared));
   HB_CUDA(cudaFuncSetAttribute(k_kstar<KID>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)((TILE_ELEMS + 8 * 64 + 64 +
@@ -191,7 +198,10 @@ int set_attrs(hb_handle_t h) {
   if ((rc = set_attrs_k<2>(h, 0))) return rc;
   HB_CUDA(cudaFuncSetAttribute(k_predict_gemm,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(SM_CS + 4 * 64 * 8)));
+                               (int)PREDICT_SMEM_BYTES));
+  HB_CUDA(cudaFuncSetAttribute(k_predict_gemm,
+                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared));
   h->attr_set = true;
   return HB_OK;
 }
@@ -614,7 +624,7 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
         default: launch_kstar<2>(Q, smem, st); break;
       }
       HB_LAUNCH_CHECK();
-      k_predict_gemm<<<dim3(nblk, Q.nqc), NTHREADS, SM_CS + 4 * 64 * 8, st>>>(Q);
+      k_predict_gemm<<<dim3(nblk, Q.nqc), NTHREADS, PREDICT_SMEM_BYTES, st>>>(Q);
       HB_LAUNCH_CHECK();
     }
     k_predict_final<<<(unsigned)((Q.nq + 255) / 256), 256, 0, st>>>(

@@ -133,7 +133,7 @@ __device__ __forceinline__ Real frag_mnmajor(const Real* tile, int blk8, int kb,
 }
 
 // Warp roles inside the 256-thread CTA for one 64x64 output tile:
-//   wk = warp >> 2 : split-K half (k-blocks [8wk, 8wk+8))
+//   wk = warp >> 2 : split-K half of every k range
 //   wq = warp & 3  : 32x32 quadrant, wm = wq >> 1 (rows), wn = wq & 1 (cols)
 // acc[fm][fn][e]: rows 32wm + 8fm + g, cols 32wn + 8fn + 2t + e.
 struct WarpPos {
@@ -149,32 +149,53 @@ struct WarpPos {
   }
 };
 
+// offset of the MN-major fragment (k-block kl, idx-block blk8) inside a buffer
+// whose rows are the contraction index and whose row-blocks hold 16 col-blocks
+__device__ __forceinline__ int mn_off(int blk8, int kl, int g, int t) {
+  return ((((kl >> 1) << 4) + (blk8 << 1) + (g >> 2)) << 5) +
+         ((((kl & 1) << 2) + t) << 2) + (g & 3);
+}
+
+// acc += A_half * B_half over the local k-blocks [kl_lo, kl_hi) of one k-half
+// (8 k-blocks of 4).  K-major operand: micro-block (blk8, kl) at
+// (blk8 * rbs + kl) * 32 (rbs = 8 in a pipeline stage, 16 in a resident tile
+// whose pointer is pre-offset by 8h micro-blocks).  MN-major operand: rows
+// 0..31 of the half, 16 col-blocks per row-block (pointer pre-offset by
+// h * 2048 in a resident tile).  The two split-K warp groups share the range.
 template <int AM, int BM>
-__device__ __forceinline__ void tile_mma(double (&acc)[4][4][2],
-                                         const double* __restrict__ As,
-                                         const double* __restrict__ Bs,
-                                         const WarpPos& w, int kb_lo = 0,
-                                         int kb_hi = 16) {
-  // the two split-K warp groups share the non-zero k-block range
-  // [kb_lo, kb_hi) evenly (callers pass the non-zero range of triangular
-  // operands so that structural zeros are never multiplied)
-  const int kmid = kb_lo + ((kb_hi - kb_lo + 1) >> 1);
-  const int k0 = w.wk ? kmid : kb_lo, k1 = w.wk ? kb_hi : kmid;
+__device__ __forceinline__ void half_mma(double (&acc)[4][4][2],
+                                         const double* __restrict__ Ah, int a_rbs,
+                                         const double* __restrict__ Bh, int b_rbs,
+                                         const WarpPos& w, int kl_lo = 0,
+                                         int kl_hi = 8) {
+  const int kmid = kl_lo + ((kl_hi - kl_lo + 1) >> 1);
+  const int k0 = w.wk ? kmid : kl_lo, k1 = w.wk ? kl_hi : kmid;
 #pragma unroll 2
-  for (int kb = k0; kb < k1; ++kb) {
+  for (int kl = k0; kl < k1; ++kl) {
     double a[4], b[4];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-      a[f] = (AM == KMAJOR) ? frag_kmajor(As, 4 * w.wm + f, kb, w.lane)
-                            : frag_mnmajor(As, 4 * w.wm + f, kb, w.lane);
-      b[f] = (BM == KMAJOR) ? frag_kmajor(Bs, 4 * w.wn + f, kb, w.lane)
-                            : frag_mnmajor(Bs, 4 * w.wn + f, kb, w.lane);
+      a[f] = (AM == KMAJOR) ? Ah[((((4 * w.wm + f) * a_rbs) + kl) << 5) + w.lane]
+                            : Ah[mn_off(4 * w.wm + f, kl, w.g, w.t)];
+      b[f] = (BM == KMAJOR) ? Bh[((((4 * w.wn + f) * b_rbs) + kl) << 5) + w.lane]
+                            : Bh[mn_off(4 * w.wn + f, kl, w.g, w.t)];
     }
 #pragma unroll
     for (int fm = 0; fm < 4; ++fm)
 #pragma unroll
       for (int fn = 0; fn < 4; ++fn) mma_884(acc[fm][fn], a[fm], b[fn]);
   }
+}
+
+// both operands are full tiles resident in shared memory (tile layout)
+template <int AM, int BM>
+__device__ __forceinline__ void resident_mma(double (&acc)[4][4][2],
+                                             const double* At, const double* Bt,
+                                             const WarpPos& w) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    half_mma<AM, BM>(acc, (AM == KMAJOR) ? At + ((8 * h) << 5) : At + h * 2048, 16,
+                     (BM == KMAJOR) ? Bt + ((8 * h) << 5) : Bt + h * 2048, 16, w);
 }
 
 __device__ __forceinline__ void acc_zero(double (&acc)[4][4][2]) {
@@ -246,63 +267,103 @@ __device__ __forceinline__ void own_to_tile(const double (&own)[2][4][2],
 }
 
 // ----------------------------------------------------- streamed tile GEMM ---
+constexpr int HALF_ELEMS = TILE_ELEMS / 2;  // one k-half of a tile (64 x 32)
+constexpr int STAGE_ELEMS = TILE_ELEMS;     // A half + B half
+constexpr int NSTAGE = 3;                   // ring = 3 x 32 KiB (fp64)
+
 struct TilePair {
-  const double* a;  // global tile for operand A (nullptr: use fixed smem A)
-  const double* b;  // global tile for operand B (nullptr: fixed smem B;
-                    //  == a: reuse the A tile)
-  int kb_lo, kb_hi; // non-zero k-block range of this product
+  const double* a;  // global tile of operand A
+  const double* b;  // global tile of operand B (== a: reuse the A half)
+  int kb_lo, kb_hi; // non-zero k-block range of this product, within [0,16)
 };
 
 struct Pipe {
-  uint64_t* full;  // [2] mbarriers
-  double* stA;     // [2][TILE_ELEMS]
-  double* stB;     // [2][TILE_ELEMS]
-  uint32_t it;     // tiles consumed so far by this CTA (uniform)
+  uint64_t* bars;    // [NSTAGE] stage barriers + [1] aux barrier
+  double* ring;      // NSTAGE x STAGE_ELEMS; also reused as R0/R1/R2 scratch
+  uint32_t parmask;  // bit s: parity the next wait on barrier s expects
 };
 
-// acc += sum_k A_k * B_k, tiles streamed from global memory with a 2-stage TMA
-// bulk-copy pipeline (tile k+1 in flight while tile k feeds the tensor pipe).
-// Caller guarantees a __syncthreads() since the last generic access to the
-// stage buffers.  `hook(k, As, Bs)` runs on every tile while it is resident.
+__device__ __forceinline__ void pipe_wait(Pipe& p, int s) {
+  mbar_wait(&p.bars[s], (p.parmask >> s) & 1u);
+  p.parmask ^= (1u << s);
+}
+// one whole tile global -> resident smem buffer on the aux barrier (thread 0)
+__device__ __forceinline__ void load_tile_async(Pipe& p, double* dst,
+                                                const double* src) {
+  mbar_expect_tx(&p.bars[NSTAGE], TILE_ELEMS * 8);
+  bulk_g2s(dst, src, TILE_ELEMS * 8, &p.bars[NSTAGE]);
+}
+
+// acc += sum_k A_k * B_k with the tiles streamed from global memory (L2) in
+// k-HALVES through a 3-stage TMA-bulk / mbarrier ring: two half-steps (= one
+// full tile product) are always in flight behind the one feeding the tensor
+// pipe.  A K-major half is 8 row-block segments of 2 KiB, an MN-major half is
+// one contiguous 16 KiB segment; warp 0's lanes issue the copies.  The ring
+// must be idle on entry (a __syncthreads() since its last generic use) and is
+// idle again on return.  hook(k, h, Ahalf) runs while a half is resident.
 template <int AM, int BM, class Fn, class Hook>
-__device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K,
-                                            Fn fn, Pipe& p,
-                                            const double* Afixed,
-                                            const double* Bfixed, Hook hook,
+__device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn,
+                                            Pipe& p, Hook hook,
                                             const WarpPos& w) {
-  constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(double);
-  auto issue = [&](int k, uint32_t itk) {
-    const TilePair tp = fn(k);
-    const int s = itk & 1;
-    const bool lb = tp.b != nullptr && tp.b != tp.a;
-    const uint32_t bytes = (tp.a ? TILE_BYTES : 0u) + (lb ? TILE_BYTES : 0u);
-    mbar_expect_tx(&p.full[s], bytes);
-    if (tp.a) bulk_g2s(p.stA + s * TILE_ELEMS, tp.a, TILE_BYTES, &p.full[s]);
-    if (lb) bulk_g2s(p.stB + s * TILE_ELEMS, tp.b, TILE_BYTES, &p.full[s]);
+  int ei = 0, ni = 0;
+  auto issue_next = [&]() {
+    while (ei < 2 * K) {
+      const int k = ei >> 1, h = ei & 1;
+      const TilePair tp = fn(k);
+      ++ei;
+      if (max(tp.kb_lo, 8 * h) >= min(tp.kb_hi, 8 * h + 8)) continue;
+      const int s = ni % NSTAGE;
+      ++ni;
+      if (w.warp == 0) {
+        double* sa = p.ring + s * STAGE_ELEMS;
+        double* sb = sa + HALF_ELEMS;
+        const bool lb = tp.b != tp.a;
+        if (w.lane == 0)
+          mbar_expect_tx(&p.bars[s], (lb ? 2u : 1u) * HALF_ELEMS * 8u);
+        __syncwarp();
+        if (AM == KMAJOR) {
+          if (w.lane < 8)
+            bulk_g2s(sa + ((w.lane * 8) << 5), tp.a + ((w.lane * 16 + 8 * h) << 5),
+                     2048, &p.bars[s]);
+        } else if (w.lane == 0) {
+          bulk_g2s(sa, tp.a + h * HALF_ELEMS, HALF_ELEMS * 8, &p.bars[s]);
+        }
+        if (lb) {
+          if (BM == KMAJOR) {
+            if (w.lane >= 8 && w.lane < 16)
+              bulk_g2s(sb + (((w.lane - 8) * 8) << 5),
+                       tp.b + (((w.lane - 8) * 16 + 8 * h) << 5), 2048, &p.bars[s]);
+          } else if (w.lane == 8) {
+            bulk_g2s(sb, tp.b + h * HALF_ELEMS, HALF_ELEMS * 8, &p.bars[s]);
+          }
+        }
+      }
+      return;
+    }
   };
-  if (threadIdx.x == 0) {
-    if (K > 0) issue(0, p.it);
-    if (K > 1) issue(1, p.it + 1);
-  }
-  for (int k = 0; k < K; ++k) {
-    const int s = p.it & 1;
-    mbar_wait(&p.full[s], (p.it >> 1) & 1);
+  issue_next();
+  issue_next();
+  issue_next();
+  int nc = 0;
+  for (int ec = 0; ec < 2 * K; ++ec) {
+    const int k = ec >> 1, h = ec & 1;
     const TilePair tp = fn(k);
-    const double* As = tp.a ? p.stA + s * TILE_ELEMS : Afixed;
-    const double* Bs = (tp.b == nullptr) ? Bfixed
-                       : (tp.b == tp.a)  ? As
-                                         : p.stB + s * TILE_ELEMS;
-    tile_mma<AM, BM>(acc, As, Bs, w, tp.kb_lo, tp.kb_hi);
-    hook(k, As, Bs);
+    const int lo = max(tp.kb_lo, 8 * h), hi = min(tp.kb_hi, 8 * h + 8);
+    if (lo >= hi) continue;
+    const int s = nc % NSTAGE;
+    ++nc;
+    pipe_wait(p, s);
+    const double* As = p.ring + s * STAGE_ELEMS;
+    const double* Bs = (tp.b == tp.a) ? As : As + HALF_ELEMS;
+    half_mma<AM, BM>(acc, As, 8, Bs, 8, w, lo - 8 * h, hi - 8 * h);
+    hook(k, h, As);
     __syncthreads();
-    if (threadIdx.x == 0 && k + 2 < K) issue(k + 2, p.it + 2);
-    ++p.it;
+    issue_next();
   }
 }
 
 struct NoHook {
-  __device__ __forceinline__ void operator()(int, const double*,
-                                             const double*) const {}
+  __device__ __forceinline__ void operator()(int, int, const double*) const {}
 };
 
 // ------------------------------------------------------------ reductions ---

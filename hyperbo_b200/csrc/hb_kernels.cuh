@@ -50,25 +50,34 @@ struct Params {
 
 constexpr int GP_STRIDE = 2 + MAX_DIM;  // [sv, nv, ls...]
 
-// shared-memory map (bytes) of the tile kernels
-constexpr int SM_BARS = 0;
+// shared-memory map (bytes) of the tile kernels.  Everything large lives in the
+// 96 KiB ring: while no stream is in flight its three 32 KiB stages double as
+// R0 (split-K exchange), R1 / R2 (resident operand / output tiles).  ~106 KiB
+// per CTA at d = 8 => 2 CTAs per SM (one CTA's epilogue / diagonal block
+// overlaps the other's tensor-pipe work).
+constexpr int SM_BARS = 0;                              // 4 mbarriers
 constexpr int SM_RED = 64;                              // 16 doubles
-constexpr int SM_STA = 192;
-constexpr int SM_STB = SM_STA + 2 * TILE_ELEMS * 8;
-constexpr int SM_CS = SM_STB + 2 * TILE_ELEMS * 8;
-constexpr int SM_PS = SM_CS + TILE_ELEMS * 8;
-constexpr int SM_VEC = SM_PS + TILE_ELEMS * 8;          // 2 x 64 doubles
-constexpr int SM_X = SM_VEC + 2 * 64 * 8;
+constexpr int SM_VEC = 192;                             // 2 x 64 doubles
+constexpr int SM_RING = 1280;                           // 3 x 32 KiB
+constexpr int SM_X = SM_RING + NSTAGE * STAGE_ELEMS * 8;
 __host__ __device__ inline int xstride(int d) { return d | 1; }
 __host__ inline size_t step_smem_bytes(int d) {
   return SM_X + 2 * 64 * xstride(d) * 8;
 }
-// the lauum/grad and predict kernels do not need Cs/Ps
-constexpr int SL_VEC = SM_CS;                           // 2 x 64 doubles
-constexpr int SL_RED2 = SL_VEC + 2 * 64 * 8;            // 8 x GP_STRIDE doubles
-constexpr int SL_X = SL_RED2 + 8 * GP_STRIDE * 8;
+// k_lauum_grad additionally keeps 8 x GP_STRIDE reduction slots after the X blocks
 __host__ inline size_t lauum_smem_bytes(int d) {
-  return SL_X + 2 * 64 * xstride(d) * 8;
+  return SM_X + 2 * 64 * xstride(d) * 8 + 8 * GP_STRIDE * 8;
+}
+constexpr size_t PREDICT_SMEM_BYTES = SM_X;
+
+__device__ __forceinline__ Pipe make_pipe(unsigned char* smem) {
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s <= NSTAGE; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  return Pipe{bars, reinterpret_cast<double*>(smem + SM_RING), 0u};
 }
 
 // ------------------------------------------------------------------ prep ---
@@ -181,6 +190,184 @@ __device__ __forceinline__ void ktile_eval(double (&own)[2][4][2],
       }
 }
 
+// ------------------------------------------- in-CTA diagonal block (64x64) ---
+// Blocked right-looking Cholesky of the SPD block held in TILE LAYOUT in `At`
+// (becomes L, strict upper zeroed) plus its inverse into `Mt` (zeroed on
+// entry), b = 16:
+//   (1) warp 0 factors the 16x16 diagonal sub-block in registers (one row per
+//       lane, column broadcast by shuffles; every lane tracks the running
+//       diagonal so the pivot needs no extra broadcast),
+//   (2) the rows below solve x L_D' = a one row per thread, while warp 7
+//       inverts L_D (needed only for the final inverse, off the critical path),
+//   (3) the trailing 16x16 blocks are updated on the tensor pipe (DMMA), one
+//       warp per block, operands read straight from the tile layout.
+// Then L^{-1} is assembled block row by block row with DMMA products.
+__device__ __forceinline__ void potrf16_warp(double* At, int b, double* rsv,
+                                             int lane) {
+  const int r = lane & 15;  // lanes 16..31 mirror lanes 0..15 (no writes)
+  double a[16], dd[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = At[elem_off(16 * b + r, 16 * b + c)];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) dd[c] = __shfl_sync(0xffffffffu, a[c], c);
+  double rsk[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const double rs = rsqrt(dd[k]);  // NaN for a negative pivot: propagates
+    rsk[k] = rs;
+    const double l = a[k] * rs;  // L[r][k]
+    a[k] = l;
+#pragma unroll
+    for (int c = k + 1; c < 16; ++c) {
+      const double lc = __shfl_sync(0xffffffffu, l, c);  // L[c][k]
+      a[c] = fma(-l, lc, a[c]);
+      dd[c] = fma(-lc, lc, dd[c]);
+    }
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      At[elem_off(16 * b + r, 16 * b + c)] = (c <= r) ? a[c] : 0.0;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) rsv[16 * b + k] = rsk[k];
+  }
+}
+
+// one row below the diagonal sub-block: x L_D' = a  (forward substitution)
+__device__ __forceinline__ void trsm16_row(double* At, int b, int row,
+                                           const double* rsv) {
+  double a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = At[elem_off(row, 16 * b + c)];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const double x = a[m] * rsv[16 * b + m];
+    a[m] = x;
+#pragma unroll
+    for (int c = m + 1; c < 16; ++c)
+      a[c] = fma(-x, At[elem_off(16 * b + c, 16 * b + m)], a[c]);  // broadcast
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) At[elem_off(row, 16 * b + c)] = a[c];
+}
+
+// W = L_D^{-1}: lane c owns column c
+__device__ __forceinline__ void trtri16_warp(const double* At, double* Mt, int b,
+                                             const double* rsv, int lane) {
+  if (lane >= 16) return;
+  const int c = lane;
+  double wv[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) wv[r] = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const double x = wv[m] * rsv[16 * b + m];
+    wv[m] = x;
+#pragma unroll
+    for (int r = m + 1; r < 16; ++r)
+      wv[r] = fma(-x, At[elem_off(16 * b + r, 16 * b + m)], wv[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) Mt[elem_off(16 * b + r, 16 * b + c)] = wv[r];
+}
+
+// 16x16 block product on the tensor pipe, one warp: c[fm][fn] (rows 8fm+g,
+// cols 8fn+2t+e of the block) += A(16 x 16) * B(16 x 16), A K-major at
+// micro-blocks (a_blk8 + fm, a_kb + kq); B K-major at (b_blk8 + fn, b_kb + kq)
+// or MN-major (rows = contraction) at k-block b_kb + kq, col-block b_blk8 + fn.
+template <int BM>
+__device__ __forceinline__ void blk16_mma(double (&c)[2][2][2], const double* At,
+                                          int a_blk8, int a_kb, const double* Bt,
+                                          int b_blk8, int b_kb, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kq = 0; kq < 4; ++kq) {
+    double a[2], bb[2];
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      a[f] = At[((((a_blk8 + f) << 4) + a_kb + kq) << 5) + lane];
+      bb[f] = (BM == KMAJOR) ? Bt[((((b_blk8 + f) << 4) + b_kb + kq) << 5) + lane]
+                             : Bt[mn_off(b_blk8 + f, b_kb + kq, g, t)];
+    }
+#pragma unroll
+    for (int fm = 0; fm < 2; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 2; ++fn) mma_884(c[fm][fn], a[fm], bb[fn]);
+  }
+}
+
+__device__ __forceinline__ void potrf64_blocked(double* At, double* Mt,
+                                                double* rsv, const WarpPos& w) {
+  for (int b = 0; b < 4; ++b) {
+    if (w.warp == 0) potrf16_warp(At, b, rsv, w.lane);
+    __syncthreads();
+    const int nbelow = 48 - 16 * b;
+    if ((int)threadIdx.x < nbelow)
+      trsm16_row(At, b, 16 * (b + 1) + threadIdx.x, rsv);
+    else if (w.warp == 7)
+      trtri16_warp(At, Mt, b, rsv, w.lane);
+    __syncthreads();
+    // trailing blocks (r16, c16), b < c16 <= r16 <= 3, one warp each
+    const int nb = 3 - b;
+    if (w.warp < nb * (nb + 1) / 2) {
+      int rr = 0, cc = w.warp;
+      while (cc > rr) { cc -= rr + 1; ++rr; }
+      const int r16 = b + 1 + rr, c16 = b + 1 + cc;
+      double c[2][2][2] = {};
+      blk16_mma<KMAJOR>(c, At, 2 * r16, 4 * b, At, 2 * c16, 4 * b, w.lane);
+#pragma unroll
+      for (int fm = 0; fm < 2; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+          double2* ptr = reinterpret_cast<double2*>(
+              At + elem_off(16 * r16 + 8 * fm + w.g, 16 * c16 + 8 * fn + 2 * w.t));
+          double2 v = *ptr;
+          v.x -= c[fm][fn][0];
+          v.y -= c[fm][fn][1];
+          *ptr = v;
+        }
+    }
+    __syncthreads();
+  }
+  // zero the strictly upper 16x16 blocks of L (stale K~ values)
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
+    const int r = e >> 6, c = e & 63;
+    if ((c >> 4) > (r >> 4)) At[elem_off(r, c)] = 0.0;
+  }
+  __syncthreads();
+  // block rows of M = L^{-1}:  M(i,j) = -W_i * sum_{k=j}^{i-1} L(i,k) M(k,j)
+  for (int i = 1; i < 4; ++i) {
+    if (w.warp < i) {
+      const int j = w.warp;
+      double tacc[2][2][2] = {};
+      for (int k = j; k < i; ++k)
+        blk16_mma<MNMAJOR>(tacc, At, 2 * i, 4 * k, Mt, 2 * j, 4 * k, w.lane);
+      // stage T in M(i,j) (tile layout) to feed it back as an MN-major operand
+#pragma unroll
+      for (int fm = 0; fm < 2; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn)
+          *reinterpret_cast<double2*>(
+              Mt + elem_off(16 * i + 8 * fm + w.g, 16 * j + 8 * fn + 2 * w.t)) =
+              make_double2(tacc[fm][fn][0], tacc[fm][fn][1]);
+      __syncwarp();
+      double racc[2][2][2] = {};
+      blk16_mma<MNMAJOR>(racc, Mt, 2 * i, 4 * i, Mt, 2 * j, 4 * i, w.lane);
+      __syncwarp();
+#pragma unroll
+      for (int fm = 0; fm < 2; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn)
+          *reinterpret_cast<double2*>(
+              Mt + elem_off(16 * i + 8 * fm + w.g, 16 * j + 8 * fn + 2 * w.t)) =
+              make_double2(-racc[fm][fn][0], -racc[fm][fn][1]);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------- step kernel --
 // One launch per block column j (j = -1 .. nblk_max-1).  State on entry:
 // L(:, <j), L(j,j), M(j,j) = L(j,j)^{-1}, z_{<=j} and rows < j of M are final.
@@ -192,7 +379,7 @@ __device__ __forceinline__ void ktile_eval(double (&own)[2][4][2],
 //                    M(i,i) = L(i,i)^{-1},  z_i = M(i,i) (r_i - sum L(i,k) z_k)
 //   then j roles   : row j of M:  M(j,c) = -M(j,j) sum_{k=c}^{j-1} L(j,k) M(k,c)
 template <int KID>
-__global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TaskDesc td = P.tasks[blockIdx.y];
   const int nblk = td.nblk;
@@ -203,24 +390,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
   if (role >= np + nt) return;
 
   const WarpPos w;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
   double* red = reinterpret_cast<double*>(smem + SM_RED);
-  double* stA = reinterpret_cast<double*>(smem + SM_STA);
-  double* stB = reinterpret_cast<double*>(smem + SM_STB);
-  double* Cs = reinterpret_cast<double*>(smem + SM_CS);
-  double* Ps = reinterpret_cast<double*>(smem + SM_PS);
   double* vec = reinterpret_cast<double*>(smem + SM_VEC);
   const int DP = xstride(P.d);
   double* xi = reinterpret_cast<double*>(smem + SM_X);
   double* xj = xi + 64 * DP;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_mbar_init();
-  }
+  Pipe pipe = make_pipe(smem);
+  double* R0 = pipe.ring;
+  double* R1 = pipe.ring + STAGE_ELEMS;
+  double* R2 = pipe.ring + 2 * STAGE_ELEMS;
   __syncthreads();
-  Pipe pipe{bars, stA, stB, 0u};
   constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(double);
 
   const double* Lt = P.Lt + td.tile_off * TILE_ELEMS;
@@ -240,24 +419,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
         acc, j - c,
         [&](int kk) {
           const int k = c + kk;
-          // M(c,c) is lower triangular: rows k'' >= cols n; as B[k''][n] all
-          // k'' contribute for some n -> full range (kept simple)
           return TilePair{Lt + (size_t)tri_idx(j, k) * TILE_ELEMS,
                           Mt + (size_t)tri_idx(k, c) * TILE_ELEMS, 0, 16};
         },
-        pipe, nullptr, nullptr, NoHook(), w);
-    splitk_exchange(acc, own, stA, w);
-    own_to_tile(own, Cs, w);
+        pipe, NoHook(), w);
+    if (threadIdx.x == 0)
+      load_tile_async(pipe, R2, Mt + (size_t)tri_idx(j, j) * TILE_ELEMS);
+    splitk_exchange(acc, own, R0, w);
+    own_to_tile(own, R1, w);  // S as [k'][n]: the MN-major B operand
     __syncthreads();
+    pipe_wait(pipe, NSTAGE);
     acc_zero(acc);
-    stream_gemm<KMAJOR, MNMAJOR>(
-        acc, 1,
-        [&](int) {
-          return TilePair{Mt + (size_t)tri_idx(j, j) * TILE_ELEMS, nullptr, 0,
-                          16};
-        },
-        pipe, nullptr, Cs, NoHook(), w);
-    splitk_exchange(acc, own, stA, w);
+    resident_mma<KMAJOR, MNMAJOR>(acc, R2, R1, w);
+    splitk_exchange(acc, own, R0, w);
 #pragma unroll
     for (int fi = 0; fi < 2; ++fi)
 #pragma unroll
@@ -265,11 +439,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
         own[fi][fn][0] = -own[fi][fn][0];
         own[fi][fn][1] = -own[fi][fn][1];
       }
-    own_to_tile(own, Ps, w);
+    own_to_tile(own, R1, w);
     fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
-      bulk_s2g(Mtw + (size_t)tri_idx(j, c) * TILE_ELEMS, Ps, TILE_BYTES);
+      bulk_s2g(Mtw + (size_t)tri_idx(j, c) * TILE_ELEMS, R1, TILE_BYTES);
       bulk_commit();
       bulk_wait_all();
     }
@@ -278,8 +452,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
 
   // ------------------------------------------------------------ panel role
   const int i = (j < 0) ? 0 : j + 1 + role;
-  const long long rowi = td.xoff + 64LL * i;
-  load_xblock(xi, P.X, rowi, min(64, td.n - 64 * i), P.d, DP, P.theta);
+  load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
+              P.theta);
   if (j >= 0) {
     load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
                 P.theta);
@@ -290,72 +464,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
           return TilePair{Lt + (size_t)tri_idx(i, k) * TILE_ELEMS,
                           Lt + (size_t)tri_idx(j, k) * TILE_ELEMS, 0, 16};
         },
-        pipe, nullptr, nullptr, NoHook(), w);
-    splitk_exchange(acc, own, stA, w);  // also orders the xi/xj loads
+        pipe, NoHook(), w);
+    if (threadIdx.x == 0)
+      load_tile_async(pipe, R2, Mt + (size_t)tri_idx(j, j) * TILE_ELEMS);
+    splitk_exchange(acc, own, R0, w);  // its barriers also publish xi / xj
     ktile_eval<KID, true>(own, xi, xj, P.d, DP, 64 * i, 64 * j, td.n, sv, 0.0,
                           w);
-    own_to_tile(own, Cs, w);
+    own_to_tile(own, R1, w);
     __syncthreads();
+    pipe_wait(pipe, NSTAGE);
     acc_zero(acc);
-    stream_gemm<KMAJOR, KMAJOR>(
-        acc, 1,
-        [&](int) {
-          return TilePair{nullptr, Mt + (size_t)tri_idx(j, j) * TILE_ELEMS, 0,
-                          16};
-        },
-        pipe, Cs, nullptr, NoHook(), w);
-    splitk_exchange(acc, own, stA, w);
-    own_to_tile(own, Ps, w);
+    resident_mma<KMAJOR, KMAJOR>(acc, R1, R2, w);  // (K - S) * M(j,j)'
+    splitk_exchange(acc, own, R0, w);
+    own_to_tile(own, R1, w);
     fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
-      bulk_s2g(Ltw + (size_t)tri_idx(i, j) * TILE_ELEMS, Ps, TILE_BYTES);
+      bulk_s2g(Ltw + (size_t)tri_idx(i, j) * TILE_ELEMS, R1, TILE_BYTES);
       bulk_commit();
+      if (role != 0) bulk_wait_all();
     }
-    if (role != 0) {
-      if (threadIdx.x == 0) bulk_wait_all();
-      return;
-    }
+    if (role != 0) return;
   }
 
   // ------------------------------------- look-ahead: factor diagonal block i
+  // A = K~(i,i) - sum_{k<=j} L(i,k) L(i,k)'.  The k = j term uses the L(i,j)
+  // tile still resident in R1; the k < j terms stream through the ring.
   // rhs partial: lane (g,t) of warp w accumulates sum_k L(i,k)[8w+g][.] z_k[.]
   double rhs_part = 0.0;
   const double* zt = P.z + td.voff;
-  auto matvec_hook = [&](int k, const double* As, const double*) {
-    const double* zk = zt + 64 * k;
-#pragma unroll 4
-    for (int cb = 0; cb < 16; ++cb)
-      rhs_part = fma(As[(((w.warp << 4) + cb) << 5) + w.lane],
-                     zk[4 * cb + w.t], rhs_part);
-  };
   acc_zero(acc);
+  if (j >= 0) {
+    resident_mma<KMAJOR, KMAJOR>(acc, R1, R1, w);
+    const double* zk = zt + 64 * j;
+#pragma unroll
+    for (int cb = 0; cb < 16; ++cb)
+      rhs_part = fma(R1[(((w.warp << 4) + cb) << 5) + w.lane], zk[4 * cb + w.t],
+                     rhs_part);
+    if (threadIdx.x == 0) bulk_wait_read_all();  // the store has read R1
+    __syncthreads();
+  }
+  auto matvec_hook = [&](int k, int h, const double* Ah) {
+    const double* zk = zt + 64 * k + 32 * h;
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb)
+      rhs_part = fma(Ah[(((w.warp << 3) + cb) << 5) + w.lane], zk[4 * cb + w.t],
+                     rhs_part);
+  };
   stream_gemm<KMAJOR, KMAJOR>(
       acc, max(j, 0),
       [&](int k) {
         const double* a = Lt + (size_t)tri_idx(i, k) * TILE_ELEMS;
         return TilePair{a, a, 0, 16};
       },
-      pipe, nullptr, nullptr, matvec_hook, w);
-  if (j >= 0) {
-    tile_mma<KMAJOR, KMAJOR>(acc, Ps, Ps, w);
-    matvec_hook(j, Ps, Ps);
-  }
-  splitk_exchange(acc, own, stA, w);
+      pipe, matvec_hook, w);
+  splitk_exchange(acc, own, R0, w);
   ktile_eval<KID, true>(own, xi, xi, P.d, DP, 64 * i, 64 * i, td.n, sv,
                         nv + JITTER, w);
-
-  // dense copies for the in-CTA factorisation (alias the stage buffers)
-  constexpr int LD = 65;
-  double* Ls = stA;  // [64][65] A, then the unscaled columns of L
-  double* Xs = stB;  // [64][65] unscaled rows of L^{-1}
-#pragma unroll
-  for (int fi = 0; fi < 2; ++fi)
-#pragma unroll
-    for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-        Ls[own_row(w, fi) * LD + own_col(w, fn, e)] = own[fi][fn][e];
+  own_to_tile(own, R1, w);  // A block in tile layout
+  for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) R2[e] = 0.0;
   // rhs = (y - m) - sum_k L(i,k) z_k
   rhs_part += __shfl_xor_sync(0xffffffffu, rhs_part, 1);
   rhs_part += __shfl_xor_sync(0xffffffffu, rhs_part, 2);
@@ -366,102 +533,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_step(Params P, int j) {
     vec[r] = yv - rhs_part;
   }
   __syncthreads();
+  potrf64_blocked(R1, R2, vec + 64, w);
 
-  // Fused unblocked Cholesky + triangular inverse, "unscaled" (LDL-like) form:
-  // thread (tr, tc) owns A[tr+16a][tc+16b] and B[tr+16a][tc+16b] (B starts as
-  // I and becomes L^{-1}); one barrier per column.
-  {
-    const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
-    double a_reg[4][4], b_reg[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        a_reg[a][b] = Ls[(tr + 16 * a) * LD + tc + 16 * b];
-        b_reg[a][b] = (tr + 16 * a == tc + 16 * b) ? 1.0 : 0.0;
-      }
-    __syncthreads();
-    for (int k = 0; k < 64; ++k) {
-      const int kq = k >> 4, kr = k & 15;
-      if (tc == kr) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (b == kq) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) Ls[(tr + 16 * a) * LD + k] = a_reg[a][b];
-          }
-      }
-      if (tr == kr) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (a == kq) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) Xs[k * LD + tc + 16 * b] = b_reg[a][b];
-          }
-      }
-      __syncthreads();
-      const double pinv = 1.0 / Ls[k * LD + k];
-      double lr[4], lc[4], xr[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) lr[a] = Ls[(tr + 16 * a) * LD + k] * pinv;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        lc[b] = Ls[(tc + 16 * b) * LD + k];
-        xr[b] = Xs[k * LD + tc + 16 * b];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        if (16 * a + 15 <= k) continue;  // rows of this register block final
-        const int r = tr + 16 * a;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = tc + 16 * b;
-          if (r > k && c > k) a_reg[a][b] = fma(-lr[a], lc[b], a_reg[a][b]);
-          if (r > k && c <= k) b_reg[a][b] = fma(-lr[a], xr[b], b_reg[a][b]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  // pivots -> 1/sqrt, log-determinant part, breakdown detection
+  // log-determinant part and breakdown detection from the diagonal of L
   double ld_part = 0.0;
   if (threadIdx.x < 64) {
-    const double p = Ls[threadIdx.x * LD + threadIdx.x];
-    vec[64 + threadIdx.x] = 1.0 / sqrt(p);
-    ld_part = 0.5 * log(p);
-    const bool bad = !(p > 0.0);
+    const double l = R1[elem_off(threadIdx.x, threadIdx.x)];
+    ld_part = log(l);
+    const bool bad = !(l > 0.0) || !isfinite(l);
     const unsigned m = __ballot_sync(0xffffffffu, bad);
     if (m && (threadIdx.x & 31) == 0)
       atomicMin(&P.bad[blockIdx.y],
                 (unsigned)(64 * i + (threadIdx.x & 32) + __ffs(m)));
   }
-  ld_part = block_sum(ld_part, red);
-  if (threadIdx.x == 0) P.logdet[td.voff / 64 + i] = ld_part;
-  // Ps may still be read by the L(i,j) bulk store
-  if (threadIdx.x == 0) bulk_wait_read_all();
-  __syncthreads();
-  const double* rs = vec + 64;
-  for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
-    const int r = e >> 6, c = e & 63;
-    const int o = elem_off(r, c);
-    Cs[o] = (c <= r) ? Ls[r * LD + c] * rs[c] : 0.0;
-    Ps[o] = (c <= r) ? Xs[r * LD + c] * rs[r] : 0.0;
-  }
   fence_async_smem();
-  __syncthreads();
+  ld_part = block_sum(ld_part, red);
   if (threadIdx.x == 0) {
-    bulk_s2g(Ltw + (size_t)tri_idx(i, i) * TILE_ELEMS, Cs, TILE_BYTES);
-    bulk_s2g(Mtw + (size_t)tri_idx(i, i) * TILE_ELEMS, Ps, TILE_BYTES);
+    P.logdet[td.voff / 64 + i] = ld_part;
+    bulk_s2g(Ltw + (size_t)tri_idx(i, i) * TILE_ELEMS, R1, TILE_BYTES);
+    bulk_s2g(Mtw + (size_t)tri_idx(i, i) * TILE_ELEMS, R2, TILE_BYTES);
     bulk_commit();
   }
-  // z_i = L(i,i)^{-1} rhs
+  // z_i = M(i,i) rhs : warp w handles rows 8w + g
   {
-    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
     double s = 0.0;
-    for (int c = q; c <= r; c += 4) s = fma(Xs[r * LD + c], vec[c], s);
+#pragma unroll
+    for (int cb = 0; cb < 16; ++cb)
+      s = fma(R2[(((w.warp << 4) + cb) << 5) + w.lane], vec[4 * cb + w.t], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (q == 0) P.z[td.voff + 64 * i + r] = s * rs[r];
+    if (w.t == 0) P.z[td.voff + 64 * i + 8 * w.warp + w.g] = s;
   }
   if (threadIdx.x == 0) bulk_wait_all();
 }
@@ -532,7 +633,7 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha(Params P) {
 //   [0] <G, K>   [1] tr G   [2+k] <G o W, ((x_k - x'_k)/l_k)^2>
 // (symmetric counterpart of an off-diagonal tile folded in by a factor 2).
 template <int KID>
-__global__ void __launch_bounds__(NTHREADS, 1) k_lauum_grad(Params P) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TaskDesc td = P.tasks[blockIdx.y];
   const int nblk = td.nblk;
@@ -542,19 +643,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum_grad(Params P) {
   while (j > i) { j -= i + 1; ++i; }
 
   const WarpPos w;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
-  double* stA = reinterpret_cast<double*>(smem + SM_STA);
-  double* stB = reinterpret_cast<double*>(smem + SM_STB);
-  double* vec = reinterpret_cast<double*>(smem + SL_VEC);
-  double* red2 = reinterpret_cast<double*>(smem + SL_RED2);
+  double* vec = reinterpret_cast<double*>(smem + SM_VEC);
   const int DP = xstride(P.d);
-  double* xi = reinterpret_cast<double*>(smem + SL_X);
+  double* xi = reinterpret_cast<double*>(smem + SM_X);
   double* xj = xi + 64 * DP;
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_mbar_init();
-  }
+  double* red2 = xj + 64 * DP;
+  Pipe pipe = make_pipe(smem);
   load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
               P.theta);
   load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
@@ -563,7 +657,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum_grad(Params P) {
   else if (threadIdx.x < 128)
     vec[threadIdx.x] = P.alpha[td.voff + 64 * j + threadIdx.x - 64];
   __syncthreads();
-  Pipe pipe{bars, stA, stB, 0u};
   const double* Mt = P.Mt + td.tile_off * TILE_ELEMS;
 
   double acc[4][4][2];
@@ -576,8 +669,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum_grad(Params P) {
         return TilePair{Mt + (size_t)tri_idx(k, i) * TILE_ELEMS,
                         Mt + (size_t)tri_idx(k, j) * TILE_ELEMS, 0, 16};
       },
-      pipe, nullptr, nullptr, NoHook(), w);
-  splitk_exchange(acc, own, stA, w);
+      pipe, NoHook(), w);
+  splitk_exchange(acc, own, pipe.ring, w);
 
   const double sv = P.theta[TH_SV];
   const double mult = (i == j) ? 1.0 : 2.0;
@@ -931,22 +1024,14 @@ __global__ void __launch_bounds__(NTHREADS) k_kstar(PredParams Q) {
   if (threadIdx.x == 0) bulk_wait_all();
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_predict_gemm(PredParams Q) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_predict_gemm(PredParams Q) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int i = Q.nblk - 1 - blockIdx.x;  // heavy rows first
   const int qc = blockIdx.y;
   const WarpPos w;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);
-  double* stA = reinterpret_cast<double*>(smem + SM_STA);
-  double* stB = reinterpret_cast<double*>(smem + SM_STB);
-  double* part = reinterpret_cast<double*>(smem + SM_CS);  // [4][64]
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_mbar_init();
-  }
+  Pipe pipe = make_pipe(smem);
+  double* part = pipe.ring + STAGE_ELEMS;  // [4][64] in R1 (ring idle by then)
   __syncthreads();
-  Pipe pipe{bars, stA, stB, 0u};
   double acc[4][4][2];
   double own[2][4][2];
   acc_zero(acc);
@@ -956,8 +1041,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict_gemm(PredParams Q) {
         return TilePair{Q.Mt + (size_t)tri_idx(i, k) * TILE_ELEMS,
                         Q.kst + ((size_t)qc * Q.nblk + k) * TILE_ELEMS, 0, 16};
       },
-      pipe, nullptr, nullptr, NoHook(), w);
-  splitk_exchange(acc, own, stA, w);
+      pipe, NoHook(), w);
+  splitk_exchange(acc, own, pipe.ring, w);
   // column sums of V o V: reduce over fi, g (lane bits 2..4), then (wm, wk)
 #pragma unroll
   for (int fn = 0; fn < 4; ++fn)
