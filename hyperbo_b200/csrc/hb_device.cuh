@@ -134,20 +134,45 @@ __device__ __forceinline__ Real frag_mnmajor(const Real* tile, int blk8, int kb,
 
 // Warp roles inside the 256-thread CTA for one 64x64 output tile:
 //   wk = warp >> 2 : split-K half of every k range
-//   wq = warp & 3  : 32x32 quadrant, wm = wq >> 1 (rows), wn = wq & 1 (cols)
+//   q              : 32x32 quadrant, wm = q >> 1 (rows), wn = q & 1 (cols)
+// Warps w and w+4 share an SM sub-partition (w & 3).  The wk = 1 warp of a
+// sub-partition takes quadrant 3 - (w & 3), so each sub-partition owns one
+// warp of quadrant q and one of 3 - q: when triangular operands let the
+// (wm = 1) or (wn = 0) warps skip half of a k range, the remaining tensor work
+// stays balanced over the four sub-partitions.
 // acc[fm][fn][e]: rows 32wm + 8fm + g, cols 32wn + 8fn + 2t + e.
 struct WarpPos {
-  int warp, lane, wk, wm, wn, g, t;
+  int warp, lane, wk, q, wm, wn, g, t;
   __device__ __forceinline__ WarpPos() {
     warp = threadIdx.x >> 5;
     lane = threadIdx.x & 31;
     wk = warp >> 2;
-    wm = (warp >> 1) & 1;
-    wn = warp & 1;
+    q = wk ? 3 - (warp & 3) : (warp & 3);
+    wm = q >> 1;
+    wn = q & 1;
     g = lane >> 2;
     t = lane & 3;
   }
 };
+
+// structural-zero flags of a tile product (per-warp k-range clipping)
+enum TriFlags {
+  TRI_NONE = 0,
+  TRI_A_KLE = 1,    // A[m][k] = 0 for k > m  (lower-triangular, K-major role)
+  TRI_A_KGE = 2,    // A[m][k] = 0 for k < m  (lower-triangular, MN-major role)
+  TRI_B_KLE = 4,    // B[k][n] = 0 for k > n
+  TRI_B_KGE = 8,    // B[k][n] = 0 for k < n
+  TRI_SYM_LOWER = 16  // symmetric output, strictly-upper quadrant not needed
+};
+// clip the k-block range [lo, hi) (units of 4, tile-global) for this warp
+__device__ __forceinline__ void tri_clip(int flags, const WarpPos& w, int& lo,
+                                         int& hi) {
+  if (flags & TRI_A_KLE) hi = min(hi, 8 * (w.wm + 1));
+  if (flags & TRI_A_KGE) lo = max(lo, 8 * w.wm);
+  if (flags & TRI_B_KLE) hi = min(hi, 8 * (w.wn + 1));
+  if (flags & TRI_B_KGE) lo = max(lo, 8 * w.wn);
+  if ((flags & TRI_SYM_LOWER) && w.wm == 0 && w.wn == 1) hi = lo;
+}
 
 // offset of the MN-major fragment (k-block kl, idx-block blk8) inside a buffer
 // whose rows are the contraction index and whose row-blocks hold 16 col-blocks
@@ -191,11 +216,17 @@ __device__ __forceinline__ void half_mma(double (&acc)[4][4][2],
 template <int AM, int BM>
 __device__ __forceinline__ void resident_mma(double (&acc)[4][4][2],
                                              const double* At, const double* Bt,
-                                             const WarpPos& w) {
+                                             const WarpPos& w,
+                                             int flags = TRI_NONE) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
-    half_mma<AM, BM>(acc, (AM == KMAJOR) ? At + ((8 * h) << 5) : At + h * 2048, 16,
-                     (BM == KMAJOR) ? Bt + ((8 * h) << 5) : Bt + h * 2048, 16, w);
+  for (int h = 0; h < 2; ++h) {
+    int lo = 8 * h, hi = 8 * h + 8;
+    tri_clip(flags, w, lo, hi);
+    if (lo < hi)
+      half_mma<AM, BM>(acc, (AM == KMAJOR) ? At + ((8 * h) << 5) : At + h * 2048,
+                       16, (BM == KMAJOR) ? Bt + ((8 * h) << 5) : Bt + h * 2048,
+                       16, w, lo - 8 * h, hi - 8 * h);
+  }
 }
 
 __device__ __forceinline__ void acc_zero(double (&acc)[4][4][2]) {
@@ -212,7 +243,7 @@ __device__ __forceinline__ void acc_zero(double (&acc)[4][4][2]) {
 __device__ __forceinline__ void splitk_exchange(double (&acc)[4][4][2],
                                                 double (&own)[2][4][2],
                                                 double* xc, const WarpPos& w) {
-  const int wq = w.warp & 3;
+  const int wq = w.q;
   // send the half this warp does NOT keep to slot (wq, dest wk = 1 - wk);
   // static register indices only (a runtime index would spill acc to local)
   {
@@ -275,6 +306,7 @@ struct TilePair {
   const double* a;  // global tile of operand A
   const double* b;  // global tile of operand B (== a: reuse the A half)
   int kb_lo, kb_hi; // non-zero k-block range of this product, within [0,16)
+  int flags;        // TriFlags: per-warp clipping for triangular operands
 };
 
 struct Pipe {
@@ -355,7 +387,11 @@ __device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn
     pipe_wait(p, s);
     const double* As = p.ring + s * STAGE_ELEMS;
     const double* Bs = (tp.b == tp.a) ? As : As + HALF_ELEMS;
-    half_mma<AM, BM>(acc, As, 8, Bs, 8, w, lo - 8 * h, hi - 8 * h);
+    {
+      int wlo = lo, whi = hi;
+      tri_clip(tp.flags, w, wlo, whi);
+      if (wlo < whi) half_mma<AM, BM>(acc, As, 8, Bs, 8, w, wlo - 8 * h, whi - 8 * h);
+    }
     hook(k, h, As);
     __syncthreads();
     issue_next();

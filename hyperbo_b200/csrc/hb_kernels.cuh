@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
         [&](int kk) {
           const int k = c + kk;
           return TilePair{Lt + (size_t)tri_idx(j, k) * TILE_ELEMS,
-                          Mt + (size_t)tri_idx(k, c) * TILE_ELEMS, 0, 16};
+                          Mt + (size_t)tri_idx(k, c) * TILE_ELEMS, 0, 16,
+                          kk == 0 ? TRI_B_KGE : TRI_NONE};
         },
         pipe, NoHook(), w);
     if (threadIdx.x == 0)
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     __syncthreads();
     pipe_wait(pipe, NSTAGE);
     acc_zero(acc);
-    resident_mma<KMAJOR, MNMAJOR>(acc, R2, R1, w);
+    resident_mma<KMAJOR, MNMAJOR>(acc, R2, R1, w, TRI_A_KLE);
     splitk_exchange(acc, own, R0, w);
 #pragma unroll
     for (int fi = 0; fi < 2; ++fi)
@@ -462,7 +463,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
         acc, j,
         [&](int k) {
           return TilePair{Lt + (size_t)tri_idx(i, k) * TILE_ELEMS,
-                          Lt + (size_t)tri_idx(j, k) * TILE_ELEMS, 0, 16};
+                          Lt + (size_t)tri_idx(j, k) * TILE_ELEMS, 0, 16,
+                          TRI_NONE};
         },
         pipe, NoHook(), w);
     if (threadIdx.x == 0)
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     __syncthreads();
     pipe_wait(pipe, NSTAGE);
     acc_zero(acc);
-    resident_mma<KMAJOR, KMAJOR>(acc, R1, R2, w);  // (K - S) * M(j,j)'
+    resident_mma<KMAJOR, KMAJOR>(acc, R1, R2, w, TRI_B_KLE);  // (K - S) M(j,j)'
     splitk_exchange(acc, own, R0, w);
     own_to_tile(own, R1, w);
     fence_async_smem();
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
   const double* zt = P.z + td.voff;
   acc_zero(acc);
   if (j >= 0) {
-    resident_mma<KMAJOR, KMAJOR>(acc, R1, R1, w);
+    resident_mma<KMAJOR, KMAJOR>(acc, R1, R1, w, TRI_SYM_LOWER);
     const double* zk = zt + 64 * j;
 #pragma unroll
     for (int cb = 0; cb < 16; ++cb)
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
       acc, max(j, 0),
       [&](int k) {
         const double* a = Lt + (size_t)tri_idx(i, k) * TILE_ELEMS;
-        return TilePair{a, a, 0, 16};
+        return TilePair{a, a, 0, 16, TRI_SYM_LOWER};
       },
       pipe, matvec_hook, w);
   splitk_exchange(acc, own, R0, w);
@@ -666,8 +668,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
       acc, nblk - i,
       [&](int kk) {
         const int k = i + kk;
+        int fl = (i == j) ? TRI_SYM_LOWER : TRI_NONE;
+        if (kk == 0) fl |= TRI_A_KGE | (i == j ? TRI_B_KGE : 0);
         return TilePair{Mt + (size_t)tri_idx(k, i) * TILE_ELEMS,
-                        Mt + (size_t)tri_idx(k, j) * TILE_ELEMS, 0, 16};
+                        Mt + (size_t)tri_idx(k, j) * TILE_ELEMS, 0, 16, fl};
       },
       pipe, NoHook(), w);
   splitk_exchange(acc, own, pipe.ring, w);
@@ -712,9 +716,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
           kern_eval<KID>(r2[fi][fn][e], sv, k, wg);
           double G = 0.5 * (own[fi][fn][e] - vec[r] * vec[64 + c]);
           if (gr >= td.n || gc >= td.n) G = 0.0;
-          g_sv = fma(mult * G, k, g_sv);
+          // off-diagonal tiles stand for their mirror image too; a diagonal
+          // tile contributes its lower triangle (x2) and its diagonal (the
+          // strictly upper part was not computed)
+          double me = mult;
+          if (i == j) me = (r > c) ? 2.0 : (r == c ? 1.0 : 0.0);
+          if (me == 0.0) G = 0.0;
+          g_sv = fma(me * G, k, g_sv);
           if (gr == gc) g_nv += G;
-          gw[fi][fn][e] = mult * G * wg;
+          gw[fi][fn][e] = me * G * wg;
         }
   }
   // block-reduce the 2 + d partial sums deterministically
@@ -1039,7 +1049,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_predict_gemm(PredParams Q) {
       acc, i + 1,
       [&](int k) {
         return TilePair{Q.Mt + (size_t)tri_idx(i, k) * TILE_ELEMS,
-                        Q.kst + ((size_t)qc * Q.nblk + k) * TILE_ELEMS, 0, 16};
+                        Q.kst + ((size_t)qc * Q.nblk + k) * TILE_ELEMS, 0, 16,
+                        k == i ? TRI_A_KLE : TRI_NONE};
       },
       pipe, NoHook(), w);
   splitk_exchange(acc, own, pipe.ring, w);
