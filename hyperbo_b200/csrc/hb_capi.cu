@@ -41,8 +41,8 @@ struct hb_handle_s {
   int64_t launches = 0;
   uint64_t clock = 0;
   Plan plans[NPLAN];
-  Buf theta, Lt, Mt, z, alpha, logdet, asum, nll_task, gpart, gtask, info, bad,
-      sums, kst, mupart, vpart, pcache;
+  Buf theta, Lt, Mt, Wt, zz, z, alpha, logdet, asum, nll_task, gpart, gtask, info, bad,
+      sums, kst, mupart, vpart, pcache, stamps;
   bool attr_set = false;
   int smem_d = -1;
   bool profiling = false;
@@ -77,7 +77,7 @@ int ensure(hb_handle_t h, Buf& b, size_t bytes) {
 }
 
 size_t total_ws(hb_handle_t h) {
-  const Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,    &h->z,    &h->alpha,
+  const Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                       &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                       &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
                       &h->vpart, &h->pcache};
@@ -157,10 +157,15 @@ int ensure_ws(hb_handle_t h, const Plan& p, bool grad) {
   if ((rc = ensure(h, h->logdet, blocks * 8))) return rc;
   if ((rc = ensure(h, h->asum, blocks * 8))) return rc;
   if ((rc = ensure(h, h->nll_task, T * 8))) return rc;
+  if ((rc = ensure(h, h->zz, T * 8))) return rc;
   if ((rc = ensure(h, h->info, T * 4))) return rc;
   if ((rc = ensure(h, h->bad, T * 4))) return rc;
   if ((rc = ensure(h, h->sums, (3 + MAX_DIM + 2) * 8))) return rc;
+#ifdef HB_STAMPS
+  if ((rc = ensure(h, h->stamps, (size_t)(p.nblk_max + 1) * T * 8 * 64 + tiles * 64 + 1024))) return rc;
+#endif
   if (grad) {
+    if ((rc = ensure(h, h->Wt, tiles * TILE_ELEMS * 8))) return rc;
     if ((rc = ensure(h, h->gpart, tiles * GP_STRIDE * 8))) return rc;
     if ((rc = ensure(h, h->gtask, T * GP_STRIDE * 8))) return rc;
   }
@@ -218,7 +223,8 @@ int check_common(hb_handle_t h, int kernel_id, int mean_id, int d) {
 }
 
 Params make_params(hb_handle_t h, const Plan& p, int kernel_id, int mean_id,
-                   const void* X, const void* y, int with_trtri) {
+                   const void* X, const void* y, int with_trtri,
+                   bool grad = false) {
   Params P;
   P.tasks = p.tasks_d;
   P.T = p.T;
@@ -231,6 +237,8 @@ Params make_params(hb_handle_t h, const Plan& p, int kernel_id, int mean_id,
   P.theta = (const double*)h->theta.p;
   P.Lt = (double*)h->Lt.p;
   P.Mt = (double*)h->Mt.p;
+  P.Wt = grad ? (double*)h->Wt.p : nullptr;
+  P.zz = (double*)h->zz.p;
   P.z = (double*)h->z.p;
   P.alpha = (double*)h->alpha.p;
   P.logdet = (double*)h->logdet.p;
@@ -240,6 +248,7 @@ Params make_params(hb_handle_t h, const Plan& p, int kernel_id, int mean_id,
   P.gtask = (double*)h->gtask.p;
   P.info = (int*)h->info.p;
   P.bad = (unsigned*)h->bad.p;
+  P.stamps = (long long*)h->stamps.p;
   return P;
 }
 
@@ -382,7 +391,7 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
 
 int hb_destroy(hb_handle_t h) {
   if (!h) return HB_ERR_BAD_ARG;
-  Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,    &h->z,    &h->alpha,
+  Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                 &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                 &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
                 &h->vpart, &h->pcache};
@@ -397,6 +406,13 @@ int hb_destroy(hb_handle_t h) {
 const char* hb_last_error(hb_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 int64_t hb_launch_count(hb_handle_t h) { return h ? h->launches : 0; }
 int64_t hb_workspace_bytes(hb_handle_t h) { return h ? (int64_t)total_ws(h) : 0; }
+
+#ifdef HB_STAMPS
+int hb_debug_stamps(hb_handle_t h, long long* host_out, int64_t n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_out, h->stamps.p, n * 8, cudaMemcpyDeviceToHost);
+}
+#endif
 
 int hb_profile_enable(hb_handle_t h, int enable) {
   if (!h) return HB_ERR_BAD_ARG;
@@ -492,7 +508,7 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
   Plan* p;
   if ((rc = get_plan(h, T, offs, d, st, &p))) return rc;
   if ((rc = ensure_ws(h, *p, true))) return rc;
-  Params P = make_params(h, *p, kernel_id, mean_id, X, y, 1);
+  Params P = make_params(h, *p, kernel_id, mean_id, X, y, 1, true);
   if ((rc = run_factor(h, *p, P, raw, warp_mask, st))) return rc;
   if (T > 0 && p->nblk_max > 0) {
     const int nt = p->nblk_max * (p->nblk_max + 1) / 2;

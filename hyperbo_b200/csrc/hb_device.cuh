@@ -333,11 +333,17 @@ __device__ __forceinline__ void load_tile_async(Pipe& p, double* dst,
 // one contiguous 16 KiB segment; warp 0's lanes issue the copies.  The ring
 // must be idle on entry (a __syncthreads() since its last generic use) and is
 // idle again on return.  hook(k, h, Ahalf) runs while a half is resident.
-template <int AM, int BM, class Fn, class Hook>
-__device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn,
-                                            Pipe& p, Hook hook,
-                                            const WarpPos& w) {
-  int ei = 0, ni = 0;
+// pre() runs right after the first three half-steps have been issued, i.e.
+// while their TMA copies are in flight (used for the X-block / vector loads).
+// tail(stage) is called ONCE, by all threads, as soon as the stream has no more
+// half-steps to issue: `stage` is then free for an extra resident load that
+// rides behind the stream (e.g. the W tile of the lauum epilogue).  Returns the
+// stage handed to tail (or -1): it is NOT idle on return.
+template <int AM, int BM, class Fn, class Hook, class Pre, class Tail>
+__device__ __forceinline__ int stream_gemm(double (&acc)[4][4][2], int K, Fn fn,
+                                           Pipe& p, Hook hook, const WarpPos& w,
+                                           Pre pre, Tail tail) {
+  int ei = 0, ni = 0, tail_stage = -1;
   auto issue_next = [&]() {
     while (ei < 2 * K) {
       const int k = ei >> 1, h = ei & 1;
@@ -372,10 +378,15 @@ __device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn
       }
       return;
     }
+    if (tail_stage < 0) {
+      tail_stage = ni % NSTAGE;
+      tail(tail_stage);
+    }
   };
   issue_next();
   issue_next();
   issue_next();
+  pre();
   int nc = 0;
   for (int ec = 0; ec < 2 * K; ++ec) {
     const int k = ec >> 1, h = ec & 1;
@@ -396,11 +407,30 @@ __device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn
     __syncthreads();
     issue_next();
   }
+  return tail_stage;
 }
 
 struct NoHook {
   __device__ __forceinline__ void operator()(int, int, const double*) const {}
 };
+struct NoPre {
+  __device__ __forceinline__ void operator()() const {}
+};
+struct NoTail {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+template <int AM, int BM, class Fn, class Hook, class Pre>
+__device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn,
+                                            Pipe& p, Hook hook, const WarpPos& w,
+                                            Pre pre) {
+  stream_gemm<AM, BM>(acc, K, fn, p, hook, w, pre, NoTail());
+}
+template <int AM, int BM, class Fn, class Hook>
+__device__ __forceinline__ void stream_gemm(double (&acc)[4][4][2], int K, Fn fn,
+                                            Pipe& p, Hook hook,
+                                            const WarpPos& w) {
+  stream_gemm<AM, BM>(acc, K, fn, p, hook, w, NoPre(), NoTail());
+}
 
 // ------------------------------------------------------------ reductions ---
 __device__ __forceinline__ double warp_sum(double v) {

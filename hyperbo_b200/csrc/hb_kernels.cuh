@@ -37,6 +37,9 @@ struct Params {
   const double* theta;
   double* Lt;       // packed tiles of L
   double* Mt;       // packed tiles of M = L^{-1} (diag tiles: inv of diag blocks)
+  double* Wt;       // packed tiles of the pair weights W (dK/dl = W D^2/l^3);
+                    // nullptr when no gradient is requested
+  double* zz;       // per task: z'z (= r' K~^{-1} r)
   double* z;        // L^{-1} r, 64-padded per task
   double* alpha;    // K~^{-1} r, 64-padded per task
   double* logdet;   // per (task, block): sum_k log L_kk of that diagonal block
@@ -46,6 +49,7 @@ struct Params {
   double* gtask;    // per task: [2 + MAX_DIM]
   int* info;        // per task: 0 or failing column + 1
   unsigned* bad;    // per task scratch: min failing column + 1, ~0u if none
+  long long* stamps;  // debug: per-CTA phase timestamps (HB_STAMPS builds only)
 };
 
 constexpr int GP_STRIDE = 2 + MAX_DIM;  // [sv, nv, ls...]
@@ -151,7 +155,8 @@ __device__ __forceinline__ void ktile_eval(double (&own)[2][4][2],
                                            const double* xi, const double* xj,
                                            int d, int DP, int row0, int col0,
                                            int n, double sv, double diag_add,
-                                           const WarpPos& w) {
+                                           const WarpPos& w,
+                                           double* wtile = nullptr) {
   double r2[2][4][2];
 #pragma unroll
   for (int fi = 0; fi < 2; ++fi)
@@ -178,16 +183,27 @@ __device__ __forceinline__ void ktile_eval(double (&own)[2][4][2],
 #pragma unroll
   for (int fi = 0; fi < 2; ++fi)
 #pragma unroll
-    for (int fn = 0; fn < 4; ++fn)
+    for (int fn = 0; fn < 4; ++fn) {
+      double wv[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int gr = row0 + own_row(w, fi), gc = col0 + own_col(w, fn, e);
         double k, wg;
         kern_eval<KID>(r2[fi][fn][e], sv, k, wg);
         if (gr == gc) k += diag_add;
-        if (gr >= n || gc >= n) k = (gr == gc) ? 1.0 : 0.0;
+        if (gr >= n || gc >= n) {
+          k = (gr == gc) ? 1.0 : 0.0;
+          wg = 0.0;  // padding never contributes to the gradient
+        }
+        wv[e] = wg;
         own[fi][fn][e] = SUB ? k - own[fi][fn][e] : k;
       }
+      // keep the pair weights for the gradient contraction (k_lauum_grad)
+      if (wtile)
+        *reinterpret_cast<double2*>(
+            wtile + elem_off(own_row(w, fi), own_col(w, fn, 0))) =
+            make_double2(wv[0], wv[1]);
+    }
 }
 
 // ------------------------------------------- in-CTA diagonal block (64x64) ---
@@ -390,6 +406,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
   if (role >= np + nt) return;
 
   const WarpPos w;
+#ifdef HB_STAMPS
+  long long sk_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  sk_[0] = clock64();
+#define HB_SK(k) sk_[k] = clock64()
+#define HB_SK_OUT(kind)                                                        \
+  if (threadIdx.x == 0 && P.stamps) {                                          \
+    long long* o = P.stamps + (((size_t)(j + 1) * P.T + blockIdx.y) * 8 +      \
+                               blockIdx.x) * 8;                                \
+    for (int q_ = 0; q_ < 7; ++q_) o[q_] = sk_[q_];                            \
+    o[7] = kind;                                                               \
+  }
+#else
+#define HB_SK(k)
+#define HB_SK_OUT(kind)
+#endif
   double* red = reinterpret_cast<double*>(smem + SM_RED);
   double* vec = reinterpret_cast<double*>(smem + SM_VEC);
   const int DP = xstride(P.d);
@@ -424,6 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
                           kk == 0 ? TRI_B_KGE : TRI_NONE};
         },
         pipe, NoHook(), w);
+    HB_SK(1);
     if (threadIdx.x == 0)
       load_tile_async(pipe, R2, Mt + (size_t)tri_idx(j, j) * TILE_ELEMS);
     splitk_exchange(acc, own, R0, w);
@@ -446,18 +478,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     if (threadIdx.x == 0) {
       bulk_s2g(Mtw + (size_t)tri_idx(j, c) * TILE_ELEMS, R1, TILE_BYTES);
       bulk_commit();
-      bulk_wait_all();
+      bulk_wait_read_all();
     }
+    HB_SK(2);
+    HB_SK_OUT(2);
     return;
   }
 
   // ------------------------------------------------------------ panel role
   const int i = (j < 0) ? 0 : j + 1 + role;
-  load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
-              P.theta);
-  if (j >= 0) {
-    load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
+  auto load_x = [&]() {
+    load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
                 P.theta);
+    if (j >= 0)
+      load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
+                  P.theta);
+  };
+  if (j < 0) load_x();
+  if (j >= 0) {
     acc_zero(acc);
     stream_gemm<KMAJOR, KMAJOR>(
         acc, j,
@@ -466,14 +504,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
                           Lt + (size_t)tri_idx(j, k) * TILE_ELEMS, 0, 16,
                           TRI_NONE};
         },
-        pipe, NoHook(), w);
+        pipe, NoHook(), w, load_x);
+    HB_SK(1);
     if (threadIdx.x == 0)
       load_tile_async(pipe, R2, Mt + (size_t)tri_idx(j, j) * TILE_ELEMS);
     splitk_exchange(acc, own, R0, w);  // its barriers also publish xi / xj
-    ktile_eval<KID, true>(own, xi, xj, P.d, DP, 64 * i, 64 * j, td.n, sv, 0.0,
-                          w);
+    ktile_eval<KID, true>(
+        own, xi, xj, P.d, DP, 64 * i, 64 * j, td.n, sv, 0.0, w,
+        P.Wt ? P.Wt + (td.tile_off + tri_idx(i, j)) * TILE_ELEMS : nullptr);
     own_to_tile(own, R1, w);
     __syncthreads();
+    HB_SK(2);
     pipe_wait(pipe, NSTAGE);
     acc_zero(acc);
     resident_mma<KMAJOR, KMAJOR>(acc, R1, R2, w, TRI_B_KLE);  // (K - S) M(j,j)'
@@ -484,9 +525,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     if (threadIdx.x == 0) {
       bulk_s2g(Ltw + (size_t)tri_idx(i, j) * TILE_ELEMS, R1, TILE_BYTES);
       bulk_commit();
-      if (role != 0) bulk_wait_all();
+      if (role != 0) bulk_wait_read_all();
     }
-    if (role != 0) return;
+    HB_SK(3);
+    if (role != 0) {
+      HB_SK_OUT(1);
+      return;
+    }
   }
 
   // ------------------------------------- look-ahead: factor diagonal block i
@@ -520,9 +565,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
         return TilePair{a, a, 0, 16, TRI_SYM_LOWER};
       },
       pipe, matvec_hook, w);
+  HB_SK(4);
   splitk_exchange(acc, own, R0, w);
-  ktile_eval<KID, true>(own, xi, xi, P.d, DP, 64 * i, 64 * i, td.n, sv,
-                        nv + JITTER, w);
+  ktile_eval<KID, true>(
+      own, xi, xi, P.d, DP, 64 * i, 64 * i, td.n, sv, nv + JITTER, w,
+      P.Wt ? P.Wt + (td.tile_off + tri_idx(i, i)) * TILE_ELEMS : nullptr);
   own_to_tile(own, R1, w);  // A block in tile layout
   for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) R2[e] = 0.0;
   // rhs = (y - m) - sum_k L(i,k) z_k
@@ -535,7 +582,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     vec[r] = yv - rhs_part;
   }
   __syncthreads();
+  HB_SK(5);
   potrf64_blocked(R1, R2, vec + 64, w);
+  HB_SK(6);
 
   // log-determinant part and breakdown detection from the diagonal of L
   double ld_part = 0.0;
@@ -566,7 +615,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if (w.t == 0) P.z[td.voff + 64 * i + 8 * w.warp + w.g] = s;
   }
-  if (threadIdx.x == 0) bulk_wait_all();
+  if (threadIdx.x == 0) bulk_wait_read_all();
+  HB_SK_OUT(0);
 }
 
 // ------------------------------------------------------------ alpha kernel --
@@ -624,6 +674,7 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha(Params P) {
       if (bad != 0xffffffffu) v = __longlong_as_double(0x7ff8000000000000LL);
       P.info[blockIdx.y] = (bad != 0xffffffffu) ? (int)bad : 0;
       P.nll_task[blockIdx.y] = v;
+      P.zz[blockIdx.y] = zz;
     }
   }
 }
@@ -641,30 +692,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
   const int nblk = td.nblk;
   const int ntile = nblk * (nblk + 1) / 2;
   if ((int)blockIdx.x >= ntile) return;
-  int i = 0, j = blockIdx.x;  // tile slot -> (i, j); heavy (small i) first
+  // launch slot -> tile: alternate heavy (small i: long k loops) and light
+  // tiles so that the CTAs sharing an SM run out of phase
+  const int slot = blockIdx.x;
+  const int tsel = (slot & 1) ? ntile - 1 - (slot >> 1) : (slot >> 1);
+  int i = 0, j = tsel;
   while (j > i) { j -= i + 1; ++i; }
 
   const WarpPos w;
+#ifdef HB_STAMPS
+  long long st_[6];
+  st_[0] = clock64();
+#define HB_STAMP(k) st_[k] = clock64()
+#else
+#define HB_STAMP(k)
+#endif
   double* vec = reinterpret_cast<double*>(smem + SM_VEC);
   const int DP = xstride(P.d);
   double* xi = reinterpret_cast<double*>(smem + SM_X);
   double* xj = xi + 64 * DP;
   double* red2 = xj + 64 * DP;
   Pipe pipe = make_pipe(smem);
-  load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
-              P.theta);
-  load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
-              P.theta);
-  if (threadIdx.x < 64) vec[threadIdx.x] = P.alpha[td.voff + 64 * i + threadIdx.x];
-  else if (threadIdx.x < 128)
-    vec[threadIdx.x] = P.alpha[td.voff + 64 * j + threadIdx.x - 64];
   __syncthreads();
   const double* Mt = P.Mt + td.tile_off * TILE_ELEMS;
+  auto load_inputs = [&]() {
+    load_xblock(xi, P.X, td.xoff + 64LL * i, min(64, td.n - 64 * i), P.d, DP,
+                P.theta);
+    load_xblock(xj, P.X, td.xoff + 64LL * j, min(64, td.n - 64 * j), P.d, DP,
+                P.theta);
+    if (threadIdx.x < 64)
+      vec[threadIdx.x] = P.alpha[td.voff + 64 * i + threadIdx.x];
+    else if (threadIdx.x < 128)
+      vec[threadIdx.x] = P.alpha[td.voff + 64 * j + threadIdx.x - 64];
+  };
 
   double acc[4][4][2];
   double own[2][4][2];
   acc_zero(acc);
-  stream_gemm<MNMAJOR, MNMAJOR>(
+  const int wstage = stream_gemm<MNMAJOR, MNMAJOR>(
       acc, nblk - i,
       [&](int kk) {
         const int k = i + kk;
@@ -673,94 +738,106 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
         return TilePair{Mt + (size_t)tri_idx(k, i) * TILE_ELEMS,
                         Mt + (size_t)tri_idx(k, j) * TILE_ELEMS, 0, 16, fl};
       },
-      pipe, NoHook(), w);
-  splitk_exchange(acc, own, pipe.ring, w);
+      pipe, NoHook(), w, load_inputs,
+      [&](int stage) {  // the W tile rides behind the last M half-steps
+        if (threadIdx.x == 0)
+          load_tile_async(pipe, pipe.ring + stage * STAGE_ELEMS,
+                          P.Wt + (td.tile_off + tri_idx(i, j)) * TILE_ELEMS);
+      });
+  HB_STAMP(2);
+  const double* Ws = pipe.ring + wstage * STAGE_ELEMS;
+  splitk_exchange(acc, own, pipe.ring + ((wstage + 1) % NSTAGE) * STAGE_ELEMS, w);
+  HB_STAMP(3);
+  pipe_wait(pipe, NSTAGE);
 
-  const double sv = P.theta[TH_SV];
+  // G = .5 (S - alpha alpha');  d nll/d l_k  needs  sum G W D_k^2  with the
+  // pair weights W saved by the factorisation (no second exp / distance pass);
+  // d nll/d noise = tr G;  d nll/d signal follows in closed form from tr G
+  // (k_reduce_final), so no kernel value is needed here at all.
   const double mult = (i == j) ? 1.0 : 2.0;
-  double g_sv = 0.0, g_nv = 0.0;
+  double g_nv = 0.0;
   double gw[2][4][2];
-  {
-    double r2[2][4][2];
 #pragma unroll
-    for (int fi = 0; fi < 2; ++fi)
+  for (int fi = 0; fi < 2; ++fi)
 #pragma unroll
-      for (int fn = 0; fn < 4; ++fn) r2[fi][fn][0] = r2[fi][fn][1] = 0.0;
-    for (int k = 0; k < P.d; ++k) {
-      double xr[2], xc[4][2];
+    for (int fn = 0; fn < 4; ++fn) {
+      const int r = own_row(w, fi), c0 = own_col(w, fn, 0);
+      const double2 wv = *reinterpret_cast<const double2*>(Ws + elem_off(r, c0));
 #pragma unroll
-      for (int fi = 0; fi < 2; ++fi) xr[fi] = xi[own_row(w, fi) * DP + k];
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + e;
+        const int gr = 64 * i + r, gc = 64 * j + c;
+        double G = 0.5 * (own[fi][fn][e] - vec[r] * vec[64 + c]);
+        // off-diagonal tiles stand for their mirror image too; a diagonal
+        // tile contributes its lower triangle (x2) and its diagonal (the
+        // strictly upper part was not computed)
+        double me = mult;
+        if (i == j) me = (r > c) ? 2.0 : (r == c ? 1.0 : 0.0);
+        if (me == 0.0 || gr >= td.n || gc >= td.n) G = 0.0;
+        if (gr == gc) g_nv += G;
+        gw[fi][fn][e] = me * G * (e ? wv.y : wv.x);
+      }
+    }
+  const double g_sv = 0.0;  // slot kept for layout; see k_reduce_final
+  HB_STAMP(4);
+  // per-thread partials for the lengthscale terms (two independent chains per
+  // dimension), then ONE batched butterfly over all partials so the shuffle /
+  // add latencies of the 2 + d reductions overlap instead of serialising
+  const int np = 2 + P.d;
+  for (int p0 = 0; p0 < np; p0 += 6) {
+    double part[6];
 #pragma unroll
-      for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) xc[fn][e] = xj[own_col(w, fn, e) * DP + k];
-#pragma unroll
-      for (int fi = 0; fi < 2; ++fi)
+    for (int u = 0; u < 6; ++u) {
+      const int p = p0 + u;
+      double v = 0.0;
+      if (p == 0) v = g_sv;
+      else if (p == 1) v = g_nv;
+      else if (p < np) {
+        const int k = p - 2;
+        double v0 = 0.0, v1 = 0.0;
+        const double xr0 = xi[own_row(w, 0) * DP + k];
+        const double xr1 = xi[own_row(w, 1) * DP + k];
 #pragma unroll
         for (int fn = 0; fn < 4; ++fn)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const double df = xr[fi] - xc[fn][e];
-            r2[fi][fn][e] = fma(df, df, r2[fi][fn][e]);
+            const double xc = xj[own_col(w, fn, e) * DP + k];
+            const double d0 = xr0 - xc, d1 = xr1 - xc;
+            v0 = fma(gw[0][fn][e], d0 * d0, v0);
+            v1 = fma(gw[1][fn][e], d1 * d1, v1);
           }
+        v = v0 + v1;
+      }
+      part[u] = v;
     }
 #pragma unroll
-    for (int fi = 0; fi < 2; ++fi)
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int fn = 0; fn < 4; ++fn)
+      for (int u = 0; u < 6; ++u)
+        part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+    if (w.lane == 0) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int r = own_row(w, fi), c = own_col(w, fn, e);
-          const int gr = 64 * i + r, gc = 64 * j + c;
-          double k, wg;
-          kern_eval<KID>(r2[fi][fn][e], sv, k, wg);
-          double G = 0.5 * (own[fi][fn][e] - vec[r] * vec[64 + c]);
-          if (gr >= td.n || gc >= td.n) G = 0.0;
-          // off-diagonal tiles stand for their mirror image too; a diagonal
-          // tile contributes its lower triangle (x2) and its diagonal (the
-          // strictly upper part was not computed)
-          double me = mult;
-          if (i == j) me = (r > c) ? 2.0 : (r == c ? 1.0 : 0.0);
-          if (me == 0.0) G = 0.0;
-          g_sv = fma(me * G, k, g_sv);
-          if (gr == gc) g_nv += G;
-          gw[fi][fn][e] = me * G * wg;
-        }
-  }
-  // block-reduce the 2 + d partial sums deterministically
-  const int np = 2 + P.d;
-  for (int p = 0; p < np; ++p) {
-    double v;
-    if (p == 0) v = g_sv;
-    else if (p == 1) v = g_nv;
-    else {
-      const int k = p - 2;
-      v = 0.0;
-      double xr[2];
-#pragma unroll
-      for (int fi = 0; fi < 2; ++fi) xr[fi] = xi[own_row(w, fi) * DP + k];
-#pragma unroll
-      for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double xc = xj[own_col(w, fn, e) * DP + k];
-#pragma unroll
-          for (int fi = 0; fi < 2; ++fi) {
-            const double df = xr[fi] - xc;
-            v = fma(gw[fi][fn][e], df * df, v);
-          }
-        }
+      for (int u = 0; u < 6; ++u)
+        if (p0 + u < np) red2[w.warp * GP_STRIDE + p0 + u] = part[u];
     }
-    v = warp_sum(v);
-    if (w.lane == 0) red2[w.warp * GP_STRIDE + p] = v;
   }
   __syncthreads();
   if ((int)threadIdx.x < np) {
-    double s = 0.0;
+    double sum = 0.0;
 #pragma unroll
-    for (int q = 0; q < NTHREADS / 32; ++q) s += red2[q * GP_STRIDE + threadIdx.x];
-    P.gpart[(td.tile_off + blockIdx.x) * GP_STRIDE + threadIdx.x] = s;
+    for (int q = 0; q < NTHREADS / 32; ++q) sum += red2[q * GP_STRIDE + threadIdx.x];
+    P.gpart[(td.tile_off + tsel) * GP_STRIDE + threadIdx.x] = sum;
   }
+#ifdef HB_STAMPS
+  HB_STAMP(5);
+  if (threadIdx.x == 0 && P.stamps) {
+    long long* o = P.stamps + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    o[0] = st_[0]; o[2] = st_[2]; o[3] = st_[3]; o[4] = st_[4]; o[5] = st_[5];
+    o[6] = smid; o[7] = nblk - i;
+  }
+#endif
 }
 
 // per-task sum of the tile partials (fixed order -> deterministic)
@@ -790,13 +867,17 @@ __global__ void k_reduce_final(Params P, double* __restrict__ out,
       else if (q == np + 1) v += 1.0;
       else if (q == 1) {  // constant: -sum alpha
         for (int b = 0; b < td.nblk; ++b) v -= P.asum[td.voff / 64 + b];
+      } else if (q == 2) {
+        // signal variance: tr(G K) = .5 (n - z'z) - (nv + eps) tr G
+        v += 0.5 * (td.n - P.zz[t]) -
+             (P.theta[TH_NV] + JITTER) * P.gtask[(size_t)t * GP_STRIDE + 1];
       } else v += P.gtask[(size_t)t * GP_STRIDE + (q - 2)];
     }
     v = block_sum(v, red);
     if (threadIdx.x == 0) {
       if (q >= 1 && q <= np && v != 0.0) {  // (an empty batch stays exactly 0)
         const int p = q - 1;
-        if (p == 1) v /= sv;                                    // <G,K>/sv
+        if (p == 1) v /= sv;                                    // tr(G K)/sv
         if (p >= 3) v *= P.theta[TH_INVLS + (p - 3)];           // /l_k
         v *= P.theta[TH_CHAIN + p];
       }
