@@ -289,8 +289,9 @@ int run_factor_k(hb_handle_t h, const Plan& p, const Params& P, cudaStream_t st)
     const int np = (j < 0) ? 1 : std::max(0, p.nblk_max - 1 - j);
     const int nt = (P.with_trtri && j >= 1) ? j : 0;
     if (np + nt == 0) continue;
-    dim3 grid(np + nt, p.T);
-    k_step<KID><<<grid, NTHREADS, smem, st>>>(P, j);
+    const int nroles = np + nt;
+    dim3 grid((unsigned)nroles * p.T);
+    k_step<KID><<<grid, NTHREADS, smem, st>>>(P, j, nroles);
     HB_LAUNCH_CHECK();
   }
   return HB_OK;

@@ -395,14 +395,27 @@ __device__ __forceinline__ void potrf64_blocked(double* At, double* Mt,
 //                    M(i,i) = L(i,i)^{-1},  z_i = M(i,i) (r_i - sum L(i,k) z_k)
 //   then j roles   : row j of M:  M(j,c) = -M(j,j) sum_{k=c}^{j-1} L(j,k) M(k,c)
 template <int KID>
-__global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j,
+                                                       int nroles) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const TaskDesc td = P.tasks[blockIdx.y];
+  // 1-D grid, longest-processing-time first: the T look-ahead CTAs (role 0:
+  // panel + diagonal block, 2-3x longer than any other role) are launched
+  // before everything else so that they never form the tail of the launch;
+  // the remaining roles stay task-major (CTAs of a task share its tiles in L2).
+  int task, role;
+  if ((int)blockIdx.x < P.T) {
+    task = blockIdx.x;
+    role = 0;
+  } else {
+    const int b = blockIdx.x - P.T;
+    task = b / (nroles - 1);
+    role = 1 + b % (nroles - 1);
+  }
+  const TaskDesc td = P.tasks[task];
   const int nblk = td.nblk;
   if (nblk == 0) return;
   const int np = (j < 0) ? 1 : max(0, nblk - 1 - j);
   const int nt = (P.with_trtri && j >= 1 && j < nblk) ? j : 0;
-  const int role = blockIdx.x;
   if (role >= np + nt) return;
 
   const WarpPos w;
@@ -412,8 +425,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
 #define HB_SK(k) sk_[k] = clock64()
 #define HB_SK_OUT(kind)                                                        \
   if (threadIdx.x == 0 && P.stamps) {                                          \
-    long long* o = P.stamps + (((size_t)(j + 1) * P.T + blockIdx.y) * 8 +      \
-                               blockIdx.x) * 8;                                \
+    long long* o = P.stamps + (((size_t)(j + 1) * P.T + task) * 8 +      \
+                               role) * 8;                                \
     for (int q_ = 0; q_ < 7; ++q_) o[q_] = sk_[q_];                            \
     o[7] = kind;                                                               \
   }
@@ -594,7 +607,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j) {
     const bool bad = !(l > 0.0) || !isfinite(l);
     const unsigned m = __ballot_sync(0xffffffffu, bad);
     if (m && (threadIdx.x & 31) == 0)
-      atomicMin(&P.bad[blockIdx.y],
+      atomicMin(&P.bad[task],
                 (unsigned)(64 * i + (threadIdx.x & 32) + __ffs(m)));
   }
   fence_async_smem();
