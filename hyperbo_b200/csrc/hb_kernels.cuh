@@ -398,19 +398,13 @@ template <int KID>
 __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j,
                                                        int nroles) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // 1-D grid, longest-processing-time first: the T look-ahead CTAs (role 0:
-  // panel + diagonal block, 2-3x longer than any other role) are launched
-  // before everything else so that they never form the tail of the launch;
-  // the remaining roles stay task-major (CTAs of a task share its tiles in L2).
-  int task, role;
-  if ((int)blockIdx.x < P.T) {
-    task = blockIdx.x;
-    role = 0;
-  } else {
-    const int b = blockIdx.x - P.T;
-    task = b / (nroles - 1);
-    role = 1 + b % (nroles - 1);
-  }
+  // 1-D grid in longest-processing-time-first order: role-major over all
+  // tasks, roles sorted by decreasing length (look-ahead CTA, panels, then the
+  // trtri roles from the longest k-loop to the shortest), so the launch tail is
+  // one short CTA instead of one long one.
+  const int role = blockIdx.x / P.T;
+  const int task = blockIdx.x - role * P.T;
+  (void)nroles;
   const TaskDesc td = P.tasks[task];
   const int nblk = td.nblk;
   if (nblk == 0) return;
