@@ -514,7 +514,7 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
   if (T > 0 && p->nblk_max > 0) {
     const int nt = p->nblk_max * (p->nblk_max + 1) / 2;
     const size_t smem = lauum_smem_bytes(d);
-    dim3 grid(nt, T);
+    dim3 grid((unsigned)nt * T);
     {
       Section sec(h, 2, st);
       switch (kernel_id) {

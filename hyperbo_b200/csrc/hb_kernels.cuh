@@ -695,14 +695,14 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha(Params P) {
 template <int KID>
 __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const TaskDesc td = P.tasks[blockIdx.y];
+  // 1-D grid, tile-major over all tasks in longest-k-loop-first order (tile
+  // slot order = increasing i = decreasing loop length): short tail
+  const int tsel = blockIdx.x / P.T;
+  const int task = blockIdx.x - tsel * P.T;
+  const TaskDesc td = P.tasks[task];
   const int nblk = td.nblk;
   const int ntile = nblk * (nblk + 1) / 2;
-  if ((int)blockIdx.x >= ntile) return;
-  // launch slot -> tile: alternate heavy (small i: long k loops) and light
-  // tiles so that the CTAs sharing an SM run out of phase
-  const int slot = blockIdx.x;
-  const int tsel = (slot & 1) ? ntile - 1 - (slot >> 1) : (slot >> 1);
+  if (tsel >= ntile) return;
   int i = 0, j = tsel;
   while (j > i) { j -= i + 1; ++i; }
 
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P) {
 #ifdef HB_STAMPS
   HB_STAMP(5);
   if (threadIdx.x == 0 && P.stamps) {
-    long long* o = P.stamps + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    long long* o = P.stamps + ((size_t)task * gridDim.x + blockIdx.x) * 8;
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     o[0] = st_[0]; o[2] = st_[2]; o[3] = st_[3]; o[4] = st_[4]; o[5] = st_[5];
