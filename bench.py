@@ -223,8 +223,9 @@ def run_ours(args):
       dist.barrier()
     torch.cuda.synchronize(dev)
 
-  def timed(trainer, from_host, steps):
-    """K steps bracketed by barrier+sync, device-timed with CUDA events."""
+  def timed(trainer, from_host, steps, graph=True):
+    """K steps bracketed by barrier+sync, device-timed with CUDA events.  The
+    launch sequence of a step is replayed from a CUDA graph (single GPU)."""
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -232,9 +233,9 @@ def run_ours(args):
     last = None
     for _ in range(steps):
       if from_host:
-        trainer.step_from_host(ds, x_host, y_host)
+        trainer.step_from_host(ds, x_host, y_host, use_graph=graph)
       else:
-        trainer.step(ds)
+        trainer.step(ds, use_graph=graph)
       last = trainer.loss()  # the per-step isfinite host read (gp.py:135-138)
       if not math.isfinite(last):
         raise FloatingPointError("non-finite loss in bench")
@@ -252,12 +253,15 @@ def run_ours(args):
   launches_per_step = eng.launch_count() - l0
   tr.loss()
   for _ in range(max(args.warmup - 1, 2)):
-    tr.step(ds)
+    tr.step(ds, use_graph=True)
     tr.loss()
   sampler = ClockSampler(local)
   sampler.start()
-  eng.h.profile_enable(True)
   ms_step, loss = timed(tr, False, args.steps)
+  # same K steps once more, eagerly, with the library's per-kernel CUDA events
+  # (events cannot be queried inside a graph): roofline numerators
+  eng.h.profile_enable(True)
+  ms_step_eager, _ = timed(tr, False, args.steps, graph=False)
   prof_ms, prof_cnt = eng.h.profile_read()
   eng.h.profile_enable(False)
   clocks = sampler.stop()
@@ -265,7 +269,7 @@ def run_ours(args):
   # ---- end-to-end run through the public trainer with HOST buffers
   tr2 = make_trainer()
   for _ in range(3):
-    tr2.step_from_host(ds, x_host, y_host)
+    tr2.step_from_host(ds, x_host, y_host, use_graph=True)
     tr2.loss()
   ms_e2e, _ = timed(tr2, True, args.steps)
 
@@ -341,7 +345,8 @@ def run_ours(args):
   line = {
       "metric": METRIC, "value": 1e3 / ms_step, "unit": "steps/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-      "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+      "ms_per_step": ms_step, "ms_per_step_eager_launches": ms_step_eager,
+      "higher_is_better": True, "scaling": "strong",
       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
       "config": {
           "workload": "configs[1]: 256 tasks x n=512 x d=8 SE-ARD + constant "

@@ -71,7 +71,7 @@ class AdamTrainer:
     self.allreduce = allreduce
     self.tie_lengthscale = tie_lengthscale
     self._graph = None
-    self._graph_ds = None
+    self._graph_key = None
 
   def _enqueue(self, ds):
     self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
@@ -83,41 +83,51 @@ class AdamTrainer:
                        self.sums, self.scal, self.lr, self.b1, self.b2,
                        self.eps, self.tie_lengthscale)
 
+  def _graphed(self, key, fn):
+    """Capture fn() once into a CUDA graph (after an eager warm-up that sizes
+    the engine workspace) and replay it afterwards."""
+    if self._graph is None or self._graph_key != key:
+      tensors = (self.raw, self.m, self.v, self.accepted, self.scal)
+      state = [t.clone() for t in tensors]
+      s = torch.cuda.Stream(device=self.eng.device)
+      s.wait_stream(torch.cuda.current_stream(self.eng.device))
+      with torch.cuda.stream(s):
+        fn()
+      torch.cuda.current_stream(self.eng.device).wait_stream(s)
+      torch.cuda.synchronize(self.eng.device)
+      for t, c in zip(tensors, state):
+        t.copy_(c)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        fn()
+      for t, c in zip(tensors, state):
+        t.copy_(c)
+      self._graph, self._graph_key = g, key
+    self._graph.replay()
+
   def step(self, ds, use_graph=False):
     """Enqueue one optimiser step on the current stream."""
     if not use_graph or self.allreduce:
       self._enqueue(ds)
-      return
-    if self._graph is None or self._graph_ds is not ds:
-      # warm up (allocates workspace), then capture the launch sequence
-      s = torch.cuda.Stream(device=self.eng.device)
-      s.wait_stream(torch.cuda.current_stream(self.eng.device))
-      state = [t.clone() for t in (self.raw, self.m, self.v, self.accepted,
-                                   self.scal)]
-      with torch.cuda.stream(s):
-        self._enqueue(ds)
-      torch.cuda.current_stream(self.eng.device).wait_stream(s)
-      torch.cuda.synchronize(self.eng.device)
-      for t, c in zip((self.raw, self.m, self.v, self.accepted, self.scal),
-                      state):
-        t.copy_(c)
-      g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
-        self._enqueue(ds)
-      for t, c in zip((self.raw, self.m, self.v, self.accepted, self.scal),
-                      state):
-        t.copy_(c)
-      self._graph, self._graph_ds = g, ds
-    self._graph.replay()
+    else:
+      self._graphed(("dev", id(ds)), lambda: self._enqueue(ds))
 
-  def step_from_host(self, ds, x_host: torch.Tensor, y_host: torch.Tensor):
+  def step_from_host(self, ds, x_host: torch.Tensor, y_host: torch.Tensor,
+                     use_graph=False):
     """One optimiser step whose batch arrives in (pinned) HOST memory: copies
     it into the packed device batch `ds` on the current stream, then steps.
     This is the shape of the reference's loop, where every step receives a
     fresh (sub-sampled) batch from the host iterator (gp.py:133)."""
-    ds.x.copy_(x_host, non_blocking=True)
-    ds.y.copy_(y_host, non_blocking=True)
-    self._enqueue(ds)
+
+    def fn():
+      ds.x.copy_(x_host, non_blocking=True)
+      ds.y.copy_(y_host, non_blocking=True)
+      self._enqueue(ds)
+
+    if not use_graph or self.allreduce:
+      fn()
+    else:
+      self._graphed(("host", id(ds), x_host.data_ptr(), y_host.data_ptr()), fn)
 
   def loss(self) -> float:
     return float(self.scal[0])  # device -> host sync (gp.py:135-138)
