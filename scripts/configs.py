@@ -1,0 +1,142 @@
+"""BASELINE.json configs C4 and C5 on one B200: correctness spot checks against
+the oracle + timings.  One JSON line per config (kept under profiles/).
+
+  C4: 24 tasks x n~U{450..550} x d=4, Matern-5/2 + constant mean: 200 Adam steps,
+      then EI over 10 000 candidates on task 0.
+  C5: 32 tasks x n=4096 x d=16 Matern-5/2: factorise-only and NLL+grad; n sweep.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hyperbo_b200.basics import definitions as defs  # noqa: E402
+from hyperbo_b200.bo_utils import acfun  # noqa: E402
+from hyperbo_b200.engine import Engine, PackedDataset  # noqa: E402
+from hyperbo_b200.gp_utils import gp, kernel, mean, utils  # noqa: E402
+from oracle import hyperbo_oracle as O  # noqa: E402  (checker)
+
+
+def ev_time(fn, iters):
+  fn()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
+      enable_timing=True)
+  e0.record()
+  for _ in range(iters):
+    fn()
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / iters
+
+
+def raw_vec(model, d):
+  ls = np.broadcast_to(np.asarray(model["lengthscale"], dtype=np.float64), (d,))
+  return np.concatenate([[model["constant"], model["signal_variance"],
+                          model["noise_variance"]], ls])
+
+
+def c4():
+  d, T = 4, 24
+  ds_np = O.make_dataset(T, 500, d, "matern52", ragged_seed=7, ragged_lo=450,
+                         ragged_hi=550)
+  model0 = O.init_raw_params(d)
+  cfg = {"method": "adam", "learning_rate": 1e-3, "max_training_step": 200,
+         "batch_size": 10**6}
+  dataset = {k: defs.SubDataset(*v) for k, v in ds_np.items()}
+  g = gp.GP(dataset, mean.constant, kernel.matern52,
+            defs.GPParams(model=dict(model0), config=dict(cfg)),
+            utils.DEFAULT_WARP_FUNC)
+  losses = []
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  g.train(callback=lambda i, m, l: losses.append(l))
+  torch.cuda.synchronize()
+  t_train = time.perf_counter() - t0
+  # oracle: first 3 losses of the same loop
+  _, ref_losses = O.infer_parameters_adam("constant", "matern52", model0, ds_np,
+                                          O.DEFAULT_WARP_FUNC, 1e-3, 3, 10**6)
+  err_loss = max(abs(a - b) / abs(b) for a, b in zip(losses[:3], ref_losses))
+  xq = np.random.Generator(np.random.PCG64(9)).random((10000, d))
+  ei = acfun.expected_improvement(model=g, sub_dataset_key=0, x_queries=xq)
+  torch.cuda.synchronize()
+  ms_ei = ev_time(lambda: acfun.expected_improvement(
+      model=g, sub_dataset_key=0, x_queries=xq), 20)
+  # includes the host->device copy of xq and the max(y) read; device-only:
+  xq_dev = torch.as_tensor(xq, device="cuda")
+  ms_ei_dev = ev_time(lambda: g.acquisition(xq_dev, 0, 1, 1.0), 20)
+  trained = {k: (np.asarray(v) if not isinstance(v, float) else v)
+             for k, v in g.params.model.items()}
+  ei_ref = O.acquisition("ei", "constant", "matern52", trained, ds_np, 0,
+                         xq[:500], O.DEFAULT_WARP_FUNC)
+  err_ei = float(np.max(np.abs(ei[:500].cpu().numpy() - ei_ref)) /
+                 np.max(np.abs(ei_ref)))
+  n0 = ds_np[0][0].shape[0]
+  flop_ei = n0 * n0 * 10000 + n0 * 10000 * (3 * d + 12)
+  print(json.dumps({
+      "config": "C4", "tasks": T, "n": "U{450..550}", "d": d,
+      "kernel": "matern52", "adam_steps": len(losses),
+      "train_s": t_train, "train_steps_per_s": len(losses) / t_train,
+      "loss_first": losses[0], "loss_last": losses[-1],
+      "loss_rel_err_vs_oracle_first3": err_loss,
+      "ei_10k_ms_public_api": ms_ei, "ei_10k_ms_device": ms_ei_dev,
+      "ei_gflops_device": flop_ei / ms_ei_dev / 1e6,
+      "ei_rel_err_vs_oracle_500q": err_ei}), flush=True)
+
+
+def c5(sweep=True):
+  eng = Engine.get()
+  d, T = 16, 32
+  out = []
+  ns = [512, 1024, 2048, 4096] if sweep else [4096]
+  for n in ns:
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = rng.random((T, n, d))
+    y = 5.0 + np.sum(np.sin(2 * np.pi * x), axis=-1, keepdims=True) \
+        + 0.1 * rng.standard_normal((T, n, 1))
+    ds = PackedDataset(list(range(T)),
+                       torch.as_tensor(x.reshape(T * n, d), device="cuda"),
+                       torch.as_tensor(y.reshape(T * n), device="cuda"),
+                       [n * t for t in range(T + 1)])
+    model = O.init_raw_params(d)
+    raw = eng.tensor(raw_vec(model, d))
+    mask = 0b110 | (((1 << d) - 1) << 3)
+    iters = 3 if n >= 2048 else 10
+    ms_f = ev_time(lambda: eng.factorize(2, 1, ds, raw, mask, want_chol=False,
+                                         want_alpha=False), iters)
+    sums = torch.empty(3 + d + 2, device="cuda", dtype=torch.float64)
+    ms_g = ev_time(lambda: eng.nll_grad(2, 1, ds, raw, mask, sums_out=sums),
+                   iters)
+    rec = {"config": "C5", "tasks": T, "n": n, "d": d, "kernel": "matern52",
+           "potrf_ms": ms_f, "potrf_tflops_n3_3": T * n**3 / 3 / ms_f / 1e9,
+           "nll_grad_ms": ms_g,
+           "nll_grad_tflops_algorithmic":
+               T * (n**3 + 4 * n * n + n * n * (3 * d + 8) +
+                    n * n * (2 * d + 6)) / ms_g / 1e9,
+           "workspace_gb": eng.workspace_bytes() / 1e9}
+    if n == ns[-1]:
+      # spot check one task against the oracle (value + gradient)
+      s1, nll_task = eng.nll_grad(2, 1, ds, raw, mask, want_task_nll=True)
+      v_ref, g_ref = O.nll_and_grad_sub_dataset("constant", "matern52", model,
+                                                x[3], y[3], O.DEFAULT_WARP_FUNC)
+      rec["nll_rel_err_task3"] = abs(float(nll_task[3]) - v_ref) / abs(v_ref)
+      one = PackedDataset([3], ds.x[3 * n:4 * n].contiguous(),
+                          ds.y[3 * n:4 * n].contiguous(), [0, n])
+      s3 = eng.nll_grad(2, 1, one, raw, mask).cpu().numpy()
+      gv = np.concatenate([[g_ref["constant"], g_ref["signal_variance"],
+                            g_ref["noise_variance"]], g_ref["lengthscale"]])
+      rec["grad_rel_err_task3"] = float(np.max(np.abs(s3[1:-1] - gv)) /
+                                        np.max(np.abs(gv)))
+    print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+  which = sys.argv[1:] or ["c4", "c5"]
+  if "c4" in which:
+    c4()
+  if "c5" in which:
+    c5()
