@@ -290,8 +290,10 @@ int run_factor_k(hb_handle_t h, const Plan& p, const Params& P, cudaStream_t st)
     const int nt = (P.with_trtri && j >= 1) ? j : 0;
     if (np + nt == 0) continue;
     const int nroles = np + nt;
-    dim3 grid((unsigned)nroles * p.T);
-    k_step<KID><<<grid, NTHREADS, smem, st>>>(P, j, nroles);
+    const int lpt = std::min(p.T, LPT_GROUP_MAX);
+    const int ngrp = (p.T + lpt - 1) / lpt;
+    dim3 grid((unsigned)nroles * lpt * ngrp);
+    k_step<KID><<<grid, NTHREADS, smem, st>>>(P, j, nroles, lpt);
     HB_LAUNCH_CHECK();
   }
   return HB_OK;
@@ -514,13 +516,15 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
   if (T > 0 && p->nblk_max > 0) {
     const int nt = p->nblk_max * (p->nblk_max + 1) / 2;
     const size_t smem = lauum_smem_bytes(d);
-    dim3 grid((unsigned)nt * T);
+    const int lpt = std::min(T, LPT_GROUP_MAX);
+    const int ngrp = (T + lpt - 1) / lpt;
+    dim3 grid((unsigned)nt * lpt * ngrp);
     {
       Section sec(h, 2, st);
       switch (kernel_id) {
-        case 0: k_lauum_grad<0><<<grid, NTHREADS, smem, st>>>(P); break;
-        case 1: k_lauum_grad<1><<<grid, NTHREADS, smem, st>>>(P); break;
-        default: k_lauum_grad<2><<<grid, NTHREADS, smem, st>>>(P); break;
+        case 0: k_lauum_grad<0><<<grid, NTHREADS, smem, st>>>(P, nt, lpt); break;
+        case 1: k_lauum_grad<1><<<grid, NTHREADS, smem, st>>>(P, nt, lpt); break;
+        default: k_lauum_grad<2><<<grid, NTHREADS, smem, st>>>(P, nt, lpt); break;
       }
       HB_LAUNCH_CHECK();
     }
