@@ -1,5 +1,6 @@
 """Name -> callable registries -- mirrors hyperbo/bo_utils/const.py:22-50."""
 from hyperbo_b200.bo_utils import acfun
+from hyperbo_b200.bo_utils import data
 from hyperbo_b200.gp_utils import kernel
 from hyperbo_b200.gp_utils import mean
 
@@ -34,3 +35,17 @@ ACFUN_SUB = {
 }
 
 EPS = 1e-6
+
+HYPERBO_DATASETS = {"random": data.random}  # const.py:54-59 (pd1 needs files)
+
+# method-name constants (const.py:63-81)
+RAND = "rand"
+STBO = "stbo"
+MTBO = "mtbo"
+STBOV = "gp"
+HBO = "hyperbo"
+HBO_SS = "hyperbo_ss"
+HBO_NLL = "hyperbo_nll"
+HBO_NLLKL = "hyperbo_nllkl"
+HBO_NLLEUC = "hyperbo_nlleuc"
+USE_HGP = [HBO_SS]

@@ -142,6 +142,64 @@ def shard_tasks(items: List, rank: int, world: int) -> List:
   return [it for t, it in enumerate(items) if t % world == rank]
 
 
+def _infer_parameters_quasi_newton(eng, kid, mid, params, dataset, warp_func,
+                                   method, key, batch_size, pack, callback,
+                                   world):
+  """L-BFGS / BFGS branches of infer_parameters (gp.py:158-191): ONE
+  sub-sampled batch (gp.py:102-107), then a host-side quasi-Newton driver whose
+  objective is the engine's batched value-and-gradient."""
+  from hyperbo_b200.basics import bfgs as _bfgs
+  from hyperbo_b200.basics import lbfgs as _lbfgs
+  batch = next(data_utils.sub_sample_dataset_iterator(key, dataset, batch_size))
+  ds = pack(batch)
+  any_x = next(iter(dataset.values())).x
+  d = int(torch.as_tensor(any_x).shape[1])
+  need_mean = mid == 1
+  template = dict(params.model)
+  raw0, mask, scalar_ls = params_utils.pack_raw(template, d, need_mean,
+                                                warp_func)
+  # optimisation variables = the model's own entries (a scalar lengthscale is
+  # ONE variable: broadcast in, summed gradient out)
+  def to_raw(v):
+    raw = np.empty(3 + d)
+    raw[0] = v[0] if need_mean else 0.0
+    raw[1], raw[2] = v[1], v[2]
+    raw[3:] = v[3] if scalar_ls else v[3:]
+    return raw
+
+  def from_raw_grad(g):
+    ls = [g[3:].sum()] if scalar_ls else list(g[3:])
+    return np.array([g[0] if need_mean else 0.0, g[1], g[2]] + ls)
+
+  v0 = np.array([raw0[0], raw0[1], raw0[2]] +
+                ([raw0[3]] if scalar_ls else list(raw0[3:])))
+
+  def val_and_grad(v):
+    sums = eng.nll_grad(kid, mid, ds, to_raw(v), mask)
+    if world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    s = sums.cpu().numpy()
+    cnt = max(s[-1], 1.0)
+    return float(s[0] / cnt), from_raw_grad(s[1:-1] / cnt)
+
+  def cb(step, model_params, loss):
+    if callback:
+      callback(step, params_utils.unpack_like(template, to_raw(model_params), d,
+                                              need_mean), loss)
+
+  if method == "lbfgs":
+    _, v, _ = _lbfgs.lbfgs(val_and_grad, v0,
+                           steps=params.config["max_training_step"],
+                           alpha=params.config.get("alpha", 1.0), callback=cb)
+  else:
+    v, _ = _bfgs.bfgs(val_and_grad, v0, tol=params.config["tol"],
+                      max_training_step=params.config["max_training_step"])
+  params.model = params_utils.unpack_like(template, to_raw(v), d, need_mean)
+  params.cache = {}
+  return params
+
+
 def infer_parameters(mean_func,
                      cov_func,
                      init_params,
@@ -172,12 +230,7 @@ def infer_parameters(mean_func,
   max_training_step = init_params.config["max_training_step"]
   if max_training_step <= 0 and method != "slice_sample":
     return init_params
-  if method != "adam":
-    if method in ("lbfgs", "bfgs"):
-      raise NotImplementedError(
-          f"method '{method}' (host-side quasi-Newton drivers, gp.py:158-191) "
-          "is a 'next' row; use objectives.nll_value_and_grad with your own "
-          "driver, or method='adam'")
+  if method not in ("adam", "lbfgs", "bfgs"):
     raise ValueError(f"Optimization method {method} is not supported.")
   if not _is_nll(objective):
     raise NotImplementedError(
@@ -197,6 +250,10 @@ def infer_parameters(mean_func,
   # data_utils.sub_sample_dataset_iterator only changes tasks with
   # n >= batch_size; when none qualifies the batch is the dataset every step.
   dataset = {k: SubDataset(*v) for k, v in dataset.items()}
+  if method != "adam":
+    return _infer_parameters_quasi_newton(
+        eng, kid, mid, params, dataset, warp_func, method, key, batch_size,
+        pack, callback, world)
   needs_subsample = any(
       torch.as_tensor(s.x).shape[0] >= batch_size for s in dataset.values())
   dataset_iter = data_utils.sub_sample_dataset_iterator(key, dataset,
@@ -402,9 +459,10 @@ class GP:
       if self.rng is None:
         self.rng = 0
         logging.info("Using default random state in GP.train.")
-      subkey = (int(self.rng) if not isinstance(self.rng, torch.Generator)
-                else self.rng)
-      if not isinstance(self.rng, torch.Generator):
+      if isinstance(self.rng, torch.Generator):
+        subkey = self.rng
+      else:
+        subkey = int(self.rng)
         self.rng = int(self.rng) + 1
     else:
       subkey = key

@@ -167,12 +167,13 @@ def test_infer_parameters_guards():
                              {0: (x, y)}) is params
   assert gp.infer_parameters(mean.constant, kernel.matern32, params, {}) is params
   params.config["max_training_step"] = 1
-  params.config["method"] = "lbfgs"
-  with pytest.raises(NotImplementedError):
-    gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)})
   params.config["method"] = "nope"
   with pytest.raises(ValueError):
     gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)})
+  params.config["method"] = "adam"
+  with pytest.raises(NotImplementedError):  # only the NLL objective is trained
+    gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)},
+                        objective=objectives.ekl)
 
 
 def test_shard_tasks_round_robin():
