@@ -534,7 +534,7 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
   }
   {
     Section sec(h, 3, st);
-    k_reduce_final<<<1, 256, 0, st>>>(P, (double*)sums_out, (double*)nll_task_out);
+    k_reduce_final<<<1, 1024, 0, st>>>(P, (double*)sums_out, (double*)nll_task_out);
     HB_LAUNCH_CHECK();
   }
   if (info_out && T > 0) {

@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_lauum_grad(Params P,
 #ifdef HB_STAMPS
   HB_STAMP(5);
   if (threadIdx.x == 0 && P.stamps) {
-    long long* o = P.stamps + ((size_t)task * gridDim.x + blockIdx.x) * 8;
+    long long* o = P.stamps + ((size_t)task * ntile_max + tsel) * 8;
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     o[0] = st_[0]; o[2] = st_[2]; o[3] = st_[3]; o[4] = st_[4]; o[5] = st_[5];
@@ -874,15 +874,17 @@ __global__ void k_reduce_task(Params P) {
 }
 
 // sums over tasks + chain rule.  out[0] = sum nll, out[1+p] = sum d nll/d raw_p,
-// out[1+P] = #non-empty tasks.  One CTA of 256 threads.
-__global__ void k_reduce_final(Params P, double* __restrict__ out,
-                               double* __restrict__ nll_task_out) {
-  __shared__ double red[16];
+// out[1+P] = #non-empty tasks.  One CTA: warp q accumulates output q (tasks
+// strided over its lanes, fixed order -> bit-reproducible), one shuffle tree.
+__global__ void __launch_bounds__(1024) k_reduce_final(
+    Params P, double* __restrict__ out, double* __restrict__ nll_task_out) {
   const int np = 3 + P.d;
+  const int nwarp = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double sv = P.theta[TH_SV];
-  for (int q = 0; q <= np + 1; ++q) {
+  for (int q = warp; q <= np + 1; q += nwarp) {
     double v = 0.0;
-    for (int t = threadIdx.x; t < P.T; t += blockDim.x) {
+    for (int t = lane; t < P.T; t += 32) {
       const TaskDesc td = P.tasks[t];
       if (td.n == 0) continue;
       if (q == 0) v += P.nll_task[t];
@@ -895,8 +897,8 @@ __global__ void k_reduce_final(Params P, double* __restrict__ out,
              (P.theta[TH_NV] + JITTER) * P.gtask[(size_t)t * GP_STRIDE + 1];
       } else v += P.gtask[(size_t)t * GP_STRIDE + (q - 2)];
     }
-    v = block_sum(v, red);
-    if (threadIdx.x == 0) {
+    v = warp_sum(v);
+    if (lane == 0) {
       if (q >= 1 && q <= np && v != 0.0) {  // (an empty batch stays exactly 0)
         const int p = q - 1;
         if (p == 1) v /= sv;                                    // tr(G K)/sv
