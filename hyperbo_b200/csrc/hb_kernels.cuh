@@ -241,6 +241,7 @@ __device__ __forceinline__ void potrf16_warp(double* At, int b, double* rsv,
       dd[c] = fma(-lc, lc, dd[c]);
     }
   }
+  __syncwarp();  // the mirrored lanes 16..31 have read these rows too
   if (lane < 16) {
 #pragma unroll
     for (int c = 0; c < 16; ++c)
