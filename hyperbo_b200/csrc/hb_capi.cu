@@ -516,9 +516,8 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
   if (T > 0 && p->nblk_max > 0) {
     const int nt = p->nblk_max * (p->nblk_max + 1) / 2;
     const size_t smem = lauum_smem_bytes(d);
-    const int lpt = std::min(T, LPT_GROUP_MAX);
-    const int ngrp = (T + lpt - 1) / lpt;
-    dim3 grid((unsigned)nt * lpt * ngrp);
+    const int lpt = 1;
+    dim3 grid((unsigned)nt * T);
     {
       Section sec(h, 2, st);
       switch (kernel_id) {
