@@ -221,6 +221,9 @@ __device__ __forceinline__ void ktile_eval(double (&own)[2][4][2],
 // Then L^{-1} is assembled block row by block row with DMMA products.
 __device__ __forceinline__ void potrf16_warp(double* At, int b, double* rsv,
                                              int lane) {
+  // (An LDL'-style variant -- reciprocal instead of rsqrt in the pivot chain,
+  // scaling deferred -- measured SLOWER, 5.6K vs 3.9K cycles per block: a
+  // single warp is bound by its instruction count here, not by the chain.)
   const int r = lane & 15;  // lanes 16..31 mirror lanes 0..15 (no writes)
   double a[16], dd[16];
 #pragma unroll
@@ -317,16 +320,25 @@ __device__ __forceinline__ void blk16_mma(double (&c)[2][2][2], const double* At
 }
 
 __device__ __forceinline__ void potrf64_blocked(double* At, double* Mt,
-                                                double* rsv, const WarpPos& w) {
+                                                double* rsv, const WarpPos& w,
+                                                long long* dbg = nullptr) {
+#ifdef HB_STAMPS
+  long long t0_ = clock64(), tp_ = 0, tt_ = 0, ts_ = 0, t1_;
+#define HB_PT(acc_) t1_ = clock64(); acc_ += t1_ - t0_; t0_ = t1_
+#else
+#define HB_PT(acc_)
+#endif
   for (int b = 0; b < 4; ++b) {
     if (w.warp == 0) potrf16_warp(At, b, rsv, w.lane);
     __syncthreads();
+    HB_PT(tp_);
     const int nbelow = 48 - 16 * b;
     if ((int)threadIdx.x < nbelow)
       trsm16_row(At, b, 16 * (b + 1) + threadIdx.x, rsv);
     else if (w.warp == 7)
       trtri16_warp(At, Mt, b, rsv, w.lane);
     __syncthreads();
+    HB_PT(tt_);
     // trailing blocks (r16, c16), b < c16 <= r16 <= 3, one warp each
     const int nb = 3 - b;
     if (w.warp < nb * (nb + 1) / 2) {
@@ -348,7 +360,11 @@ __device__ __forceinline__ void potrf64_blocked(double* At, double* Mt,
         }
     }
     __syncthreads();
+    HB_PT(ts_);
   }
+#ifdef HB_STAMPS
+  if (dbg && threadIdx.x == 0) { dbg[0] = tp_; dbg[1] = tt_; dbg[2] = ts_; dbg[3] = clock64(); }
+#endif
   // zero the strictly upper 16x16 blocks of L (stale K~ values)
   for (int e = threadIdx.x; e < TILE_ELEMS; e += NTHREADS) {
     const int r = e >> 6, c = e & 63;
@@ -599,8 +615,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_step(Params P, int j,
   }
   __syncthreads();
   HB_SK(5);
-  potrf64_blocked(R1, R2, vec + 64, w);
+#ifdef HB_STAMPS
+  __shared__ long long pdbg_[4];
+  potrf64_blocked(R1, R2, vec + 64, w, pdbg_);
   HB_SK(6);
+  if (threadIdx.x == 0) { sk_[1] = pdbg_[0]; sk_[2] = pdbg_[1]; sk_[3] = pdbg_[2]; sk_[4] = sk_[6] - pdbg_[3]; }
+#else
+  potrf64_blocked(R1, R2, vec + 64, w);
+#endif
 
   // log-determinant part and breakdown detection from the diagonal of L
   double ld_part = 0.0;
