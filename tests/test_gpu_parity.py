@@ -179,6 +179,29 @@ def test_non_pd_sets_info_and_nan_without_raising(eng):
   assert np.isnan(sums[0])  # the mean loss is NaN -> the host loop stops
 
 
+def test_many_small_ragged_tasks(eng):
+  # T > 256 exercises the grouped launch order of k_step; sizes straddle the
+  # 64-point tile edge (1 and 2 block columns), incl. n = 1 and n = 64
+  rng = np.random.default_rng(11)
+  ns = [int(v) for v in rng.integers(1, 130, 300)] + [1, 64, 65, 128]
+  d = 2
+  ds_np = {t: O.make_task(t, n, d, "matern52", surrogate=True)
+           for t, n in enumerate(ns)}
+  model = O.init_raw_params(d)
+  kid, mid = _ids("matern52", "constant")
+  sums, nll_task = eng.nll_grad(kid, mid, _pack(eng, ds_np), H.raw_vec(model, d),
+                                H.default_mask(d), want_task_nll=True)
+  sums = sums.cpu().numpy()
+  v_ref, g_ref = O.nll_value_and_grad("constant", "matern52", model, ds_np, WF)
+  T = len(ns)
+  assert sums[-1] == T
+  assert abs(sums[0] / T - v_ref) < TOL_NLL * abs(v_ref)
+  assert H.rel(sums[1:-1] / T, H.grad_vec(g_ref, d)) < TOL_GRAD
+  for t in (0, 150, 299, 300, 303):
+    ref = O.nll_sub_dataset("constant", "matern52", model, *ds_np[t], warp_func=WF)
+    assert abs(nll_task[t].item() - ref) < 1e-9 * max(1.0, abs(ref))
+
+
 def test_large_n_blocked_path(eng):
   # 17 block columns, ragged second task
   ns, d = [1040, 777], 6
