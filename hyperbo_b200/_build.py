@@ -38,8 +38,9 @@ def _run(cmd):
 
 def build(force: bool = False, verbose: bool = False) -> None:
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-  cu_src = [os.path.join(CSRC, f) for f in ("hb_capi.cu", "hb_kernels.cuh",
-                                            "hb_device.cuh")]
+  cu_src = [os.path.join(CSRC, f) for f in (
+      "hb_capi.cu", "hb_common.cuh", "hb_device.inc", "hb_kernels.inc",
+      "hb_host.inc")]
   hdr = os.path.join(HERE, "..", "include", "hyperbo_b200.h")
   if force or _newer(LIB, cu_src + [hdr]):
     cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "hb_capi.cu")]

@@ -20,6 +20,21 @@ JITTER = 1e-6  # basics/linalg.py:42 of the reference
 
 _lock = threading.Lock()
 _engines: Dict[Tuple[int, torch.dtype], "Engine"] = {}
+_default_dtype = torch.float64
+
+
+def set_default_dtype(dtype) -> None:
+  """Engine precision used by the API mirror (gp_utils / bo_utils / basics):
+  torch.float64 (default; fp64 DMMA tile products) or torch.float32 (the
+  reference's JAX default; 3xTF32 tile products)."""
+  global _default_dtype
+  if dtype not in DTYPES:
+    raise ValueError("engine dtype must be torch.float64 or torch.float32")
+  _default_dtype = dtype
+
+
+def get_default_dtype():
+  return _default_dtype
 
 
 def _load_ext():
@@ -55,7 +70,8 @@ class PackedDataset:
 class Engine:
   """One C-ABI handle per (device, dtype)."""
 
-  def __init__(self, device: Optional[int] = None, dtype=torch.float64):
+  def __init__(self, device: Optional[int] = None, dtype=None):
+    dtype = dtype or _default_dtype
     if not torch.cuda.is_available():
       raise RuntimeError("hyperbo_b200 needs a CUDA device (no CPU fallback)")
     self._C = _load_ext()
@@ -70,7 +86,8 @@ class Engine:
 
   # ------------------------------------------------------------- helpers --
   @staticmethod
-  def get(device: Optional[int] = None, dtype=torch.float64) -> "Engine":
+  def get(device: Optional[int] = None, dtype=None) -> "Engine":
+    dtype = dtype or _default_dtype
     if device is None:
       if not torch.cuda.is_available():
         raise RuntimeError("hyperbo_b200 needs a CUDA device (no CPU fallback)")
@@ -214,7 +231,7 @@ class Engine:
     y = self.tensor(y).reshape(-1)
     raw = self.tensor(raw)
     nbytes = int(self.h.predictor_bytes(n))
-    cache = torch.empty((nbytes // 8,), device=self.device, dtype=torch.float64)
+    cache = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
     chol = torch.empty((n, n), device=self.device, dtype=self.dtype)
     kinvy = torch.empty((n, 1), device=self.device, dtype=self.dtype)
     nll = torch.zeros((1,), device=self.device, dtype=self.dtype)
