@@ -202,15 +202,18 @@ def run_ours(args):
   torch.cuda.set_device(local)
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-  eng = Engine.get(local)
+  f32 = args.dtype == "f32"
+  tdt = torch.float32 if f32 else torch.float64
+  esz = 4 if f32 else 8
+  eng = Engine.get(local, dtype=tdt)
   dev = eng.device
 
   T, n, d = T_TASKS, N_PTS, DIM
   x_all, y_all = synthetic_batch(T, n, d)
   mine = shard_tasks(list(range(T)), rank, world)  # strong scaling
   Tl = len(mine)
-  x_host = torch.from_numpy(np.ascontiguousarray(x_all[mine].reshape(Tl * n, d))).pin_memory()
-  y_host = torch.from_numpy(np.ascontiguousarray(y_all[mine].reshape(Tl * n))).pin_memory()
+  x_host = torch.from_numpy(np.ascontiguousarray(x_all[mine].reshape(Tl * n, d))).to(tdt).pin_memory()
+  y_host = torch.from_numpy(np.ascontiguousarray(y_all[mine].reshape(Tl * n))).to(tdt).pin_memory()
   ds = PackedDataset(mine, x_host.to(dev), y_host.to(dev),
                      [n * t for t in range(Tl + 1)])
   mask = 0b110 | (((1 << d) - 1) << 3)
@@ -278,9 +281,12 @@ def run_ours(args):
       dist.destroy_process_group()
     return
 
-  # ---- roofline denominators: measured fp64 tensor peak (cuBLAS DGEMM)
-  a = torch.randn(8192, 8192, device=dev, dtype=torch.float64)
-  b = torch.randn(8192, 8192, device=dev, dtype=torch.float64)
+  # ---- roofline denominators: measured tensor peak of the engine's precision:
+  # cuBLAS DGEMM for fp64; cuBLAS TF32 GEMM / 3 for the fp32 engine (3xTF32)
+  if f32:
+    torch.backends.cuda.matmul.allow_tf32 = True
+  a = torch.randn(8192, 8192, device=dev, dtype=tdt)
+  b = torch.randn(8192, 8192, device=dev, dtype=tdt)
   for _ in range(2):
     a @ b
   best = 1e9
@@ -293,12 +299,14 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     best = min(best, s0.elapsed_time(s1))
   dgemm_tf = 2 * 8192**3 / best / 1e9
+  if f32:
+    dgemm_tf /= 3.0
   del a, b
 
   fl = algorithmic_flops(Tl, n, d)
   traffic = None
   tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-  if os.path.exists(tpath):
+  if os.path.exists(tpath) and not f32:
     try:
       traffic = json.load(open(tpath)).get("k_lauum_grad_dram_bytes_per_launch")
     except Exception:
@@ -317,8 +325,10 @@ def run_ours(args):
       "kernel": "k_lauum_grad (largest single launch: K~^-1 = M'M tiles on the "
                 "fp64 tensor pipe + gradient contraction)",
       "traffic": traffic,
-      "peak_source": "in-run cuBLAS DGEMM 8192^3 best of 5 (fp64 tensor pipe; "
-                     "MEASURED_PEAKS.json holds no fp64 figure)",
+      "peak_source": ("in-run cuBLAS TF32 GEMM 8192^3 best of 5, divided by 3 "
+                      "(the fp32 engine spends 3 TF32 MMAs per product)" if f32
+                      else "in-run cuBLAS DGEMM 8192^3 best of 5 (fp64 tensor "
+                      "pipe; MEASURED_PEAKS.json holds no fp64 figure)"),
       "flops_per_launch": fl["lauum_grad"],
   })
   roofline_factor = roof(fl["factor_launches"], prof_ms[0], prof_cnt[0]) or {}
@@ -336,32 +346,34 @@ def run_ours(args):
   cpu = None
   if not args.no_cpu_baseline:
     sample = 32
-    v, dt_s, cores = cpu_port_steps_per_sec(sample, 3, 1)
+    v, dt_s, cores = cpu_port_steps_per_sec(sample, 3, 1, args.dtype)
     cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
            "sample": f"{sample} of {T} tasks x 3 steps ({dt_s:.3f} s/step), "
                      f"scaled x{T // sample}; torch-CPU port of the reference "
-                     "step, fp64, task-batched"}
+                     f"step, {args.dtype}, task-batched"}
 
   line = {
       "metric": METRIC, "value": 1e3 / ms_step, "unit": "steps/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": ms_step, "ms_per_step_eager_launches": ms_step_eager,
       "higher_is_better": True, "scaling": "strong",
-      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+      "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
       "config": {
-          "workload": "configs[1]: 256 tasks x n=512 x d=8 SE-ARD + constant "
-                      "mean, fp64 NLL+grad+Adam step (tasks sharded t%N over "
+          "workload": ("configs[2]" if f32 else "configs[1]") +
+                      ": 256 tasks x n=512 x d=8 SE-ARD + constant mean, " +
+                      ("fp32" if f32 else "fp64") +
+                      " NLL+grad+Adam step (tasks sharded t%N over "
                       "N GPUs, one all-reduce of P+2 scalars per step)",
           "tasks": T, "n": n, "d": d, "tasks_per_gpu": Tl, "lr": LR,
           "l2_policy": "no explicit flush: each step streams its packed L and "
                        "L^-1 tiles (%.0f MB per GPU) through the 126 MB L2, so "
                        "no step starts with its working set resident"
-                       % (2 * Tl * 36 * 32768 / 1e6)},
+                       % (3 * Tl * 36 * 4096 * esz / 1e6)},
       "final_loss": loss,
       "clocks": clocks,
       "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
-              "h2d_bytes_per_step": int(x_host.numel() * 8 + y_host.numel() * 8),
-              "d2h_bytes_per_step": 8},
+              "h2d_bytes_per_step": int((x_host.numel() + y_host.numel()) * esz),
+              "d2h_bytes_per_step": esz},
       "gpu_launches": int(launches_per_step * args.steps),
       "gpu_launches_per_step": int(launches_per_step),
       "roofline": roofline,
@@ -386,6 +398,9 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                  help="engine precision: f64 = BASELINE configs[1] (default), "
+                       "f32 = configs[2]")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
   if args.impl == "reference":

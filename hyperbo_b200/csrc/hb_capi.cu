@@ -190,6 +190,7 @@ struct Section {
 // .inc files are compiled twice with Real = double (hb::f64, DMMA tile
 // products) and Real = float (hb::f32, 3xTF32 tile products).
 #define HB_F64 1
+#define HB_MIN_CTAS 2
 namespace hb { namespace f64 {
 using Real = double;
 using Real2 = double2;
@@ -199,7 +200,9 @@ __device__ __forceinline__ Real2 make_real2(Real a, Real b) { return make_double
 #include "hb_host.inc"
 } }  // namespace hb::f64
 #undef HB_F64
+#undef HB_MIN_CTAS
 #define HB_F64 0
+#define HB_MIN_CTAS 3
 namespace hb { namespace f32 {
 using Real = float;
 using Real2 = float2;
