@@ -53,6 +53,9 @@ enum hb_status {
   HB_ERR_NO_DEVICE = 4
 };
 
+/* HB_F64: fp64 DMMA tile products (1e-10 parity with the fp64 oracle).
+ * HB_F32: fp32 storage, 3xTF32 tensor-core tile products (the reference's JAX
+ * default precision). */
 enum hb_dtype { HB_F64 = 0, HB_F32 = 1 };
 
 /* gp_utils/kernel.py:63-123 */
