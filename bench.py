@@ -233,15 +233,17 @@ def run_ours(args):
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    last = None
     for _ in range(steps):
-      if from_host:
-        trainer.step_from_host(ds, x_host, y_host, use_graph=graph)
-      else:
-        trainer.step(ds, use_graph=graph)
-      last = trainer.loss()  # the per-step isfinite host read (gp.py:135-138)
-      if not math.isfinite(last):
+      # one read-back of the loss per step (the isfinite host check of
+      # gp.py:135-138), pipelined one step behind the enqueue
+      prev = trainer.step_pipelined(ds, x_host if from_host else None,
+                                    y_host if from_host else None,
+                                    use_graph=graph)
+      if prev is not None and not math.isfinite(prev):
         raise FloatingPointError("non-finite loss in bench")
+    last = trainer.flush()
+    if not math.isfinite(last):
+      raise FloatingPointError("non-finite loss in bench")
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)

@@ -74,6 +74,9 @@ class AdamTrainer:
     self._graph = None
     self._graph_key = None
     self._graph_failed = False
+    self._loss_pin = None
+    self._loss_evt = None
+    self._nsteps = 0
 
   def _enqueue(self, ds):
     self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
@@ -148,6 +151,42 @@ class AdamTrainer:
 
   def loss(self) -> float:
     return float(self.scal[0])  # device -> host sync (gp.py:135-138)
+
+  # ---- pipelined loss read-back -------------------------------------------
+  # The reference reads the loss on the host after every step (gp.py:135-142).
+  # The Adam kernel carries the same accept / stop logic on the device
+  # (scal[2]: once a loss is non-finite nothing is updated any more), so the
+  # host may run ONE step ahead: step k+1 is enqueued before the loss of step k
+  # is read from pinned memory.  Still one read-back per step, but the GPU never
+  # idles while the host marshals the next step.
+  def step_pipelined(self, ds, x_host=None, y_host=None, use_graph=False):
+    """Enqueue a step (optionally from host buffers) and return the loss of
+    the PREVIOUS step (None on the first call)."""
+    if self._loss_pin is None:
+      self._loss_pin = [torch.zeros(1, dtype=self.eng.dtype).pin_memory()
+                        for _ in range(2)]
+      self._loss_evt = [torch.cuda.Event() for _ in range(2)]
+    if x_host is not None:
+      self.step_from_host(ds, x_host, y_host, use_graph=use_graph)
+    else:
+      self.step(ds, use_graph=use_graph)
+    slot = self._nsteps & 1
+    self._loss_pin[slot].copy_(self.scal[0:1], non_blocking=True)
+    self._loss_evt[slot].record(torch.cuda.current_stream(self.eng.device))
+    self._nsteps += 1
+    if self._nsteps == 1:
+      return None
+    prev = (self._nsteps - 2) & 1
+    self._loss_evt[prev].synchronize()
+    return float(self._loss_pin[prev][0])
+
+  def flush(self):
+    """Loss of the last enqueued step (waits for it)."""
+    if self._nsteps == 0:
+      return None
+    last = (self._nsteps - 1) & 1
+    self._loss_evt[last].synchronize()
+    return float(self._loss_pin[last][0])
 
   @property
   def stopped(self) -> bool:
@@ -290,20 +329,37 @@ def infer_parameters(mean_func,
 
   ds = static_ds
   ran = False
-  for i in range(max_training_step):
-    if needs_subsample:
-      ds = pack(next(dataset_iter))
-    trainer.step(ds, use_graph=not needs_subsample)
-    ran = True
-    current_loss = trainer.loss()
+
+  def check(i, current_loss):
+    """gp.py:135-142; returns False when the loop must stop."""
     if math.isnan(current_loss) and i == 0:
       raise ValueError("Encountered NaN in loss function. current_loss = "
                        f"{current_loss}.")
     if not math.isfinite(current_loss):
       logging.info(msg=f"{method} stopped at step {i} due to instability.")
-      break
-    if callback:
-      callback(i, to_model(trainer.accepted), current_loss)
+      return False
+    return True
+
+  if callback is None and not needs_subsample:
+    # one step ahead of the loss read-back (see AdamTrainer.step_pipelined)
+    for i in range(max_training_step):
+      prev = trainer.step_pipelined(ds, use_graph=True)
+      ran = True
+      if prev is not None and not check(i - 1, prev):
+        break
+    else:
+      check(max_training_step - 1, trainer.flush())
+  else:
+    for i in range(max_training_step):
+      if needs_subsample:
+        ds = pack(next(dataset_iter))
+      trainer.step(ds, use_graph=not needs_subsample)
+      ran = True
+      current_loss = trainer.loss()
+      if not check(i, current_loss):
+        break
+      if callback:
+        callback(i, to_model(trainer.accepted), current_loss)
   if ran:
     final = trainer.accepted
     if not trainer.stopped:
