@@ -68,7 +68,9 @@ def test_golden_fixtures(eng, name):
 
 @pytest.mark.parametrize("cov", O.KERNELS)
 @pytest.mark.parametrize("ns,d", [([1], 1), ([63, 64, 65], 2), ([200, 5, 129], 5),
-                                  ([512, 300], 8), ([96], 32)])
+                                  ([512, 300], 8), ([96], 32),
+                                  # d > 12: X blocks staged in a ring stage
+                                  ([130, 70, 300], 16), ([100, 65], 30)])
 def test_nll_grad_vs_oracle(eng, cov, ns, d):
   ds_np = {t: O.make_task(7 * len(ns) + t, n, d, cov) for t, n in enumerate(ns)}
   model = O.init_raw_params(d)
