@@ -400,11 +400,16 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--tasks", type=int, default=None,
+                  help="experiments only: total task count instead of 256")
   ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                   help="engine precision: f64 = BASELINE configs[1] (default), "
                        "f32 = configs[2]")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
+  if args.tasks:
+    global T_TASKS
+    T_TASKS = args.tasks
   if args.impl == "reference":
     run_reference(args)
   else:

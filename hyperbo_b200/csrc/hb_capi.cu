@@ -2,6 +2,7 @@
 // arena and kernel launches.  Everything is enqueued on the caller's stream.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,8 +43,10 @@ struct hb_handle_s {
   uint64_t clock = 0;
   Plan plans[NPLAN];
   Buf theta, Lt, Mt, Wt, zz, z, alpha, logdet, asum, nll_task, gpart, gtask, info, bad,
-      sums, kst, mupart, vpart, pcache, stamps;
+      sums, kst, mupart, vpart, pcache, stamps, pre;
   bool attr_set = false;
+  int pre_override = -1;       // HB_PRE env: force the k_step pre roles off / on
+  long long pre_cta_limit = 0; // pre roles on when T * (nblk_max + 1) <= this
   int smem_d = -1;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[HB_PROFILE_SECTIONS];
@@ -80,7 +83,7 @@ size_t total_ws(hb_handle_t h) {
   const Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                       &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                       &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
-                      &h->vpart, &h->pcache};
+                      &h->vpart, &h->pcache, &h->pre};
   size_t s = 0;
   for (auto* b : all) s += b->cap;
   for (auto& p : h->plans) s += p.tasks_cap;
@@ -240,6 +243,15 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   hb_handle_t h = new hb_handle_s();
   h->device = device;
   h->dtype = dtype;
+  if (const char* e = getenv("HB_PRE")) h->pre_override = atoi(e) ? 1 : 0;
+  {
+    cudaDeviceProp prop;
+    // CTA slots of one wave (2 resident CTAs per SM in fp64, 3 in fp32)
+    h->pre_cta_limit = cudaGetDeviceProperties(&prop, device) == cudaSuccess
+                           ? 2LL * prop.multiProcessorCount * (dtype == HB_F64 ? 2 : 3)
+                           : 592;
+    if (const char* e = getenv("HB_PRE_LIMIT")) h->pre_cta_limit = atoll(e);
+  }
   *out = h;
   return HB_OK;
 }
@@ -249,7 +261,7 @@ int hb_destroy(hb_handle_t h) {
   Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                 &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                 &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
-                &h->vpart, &h->pcache};
+                &h->vpart, &h->pcache, &h->pre};
   for (auto* b : all)
     if (b->p) cudaFree(b->p);
   for (auto& p : h->plans)

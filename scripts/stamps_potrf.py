@@ -4,7 +4,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = "/tmp/libhb_stamps.so"
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
-                       "-Xcompiler", "-fPIC", "-shared", "-DHB_STAMPS", "-o", so,
+                       "-Xcompiler", "-fPIC", "-shared", "-DHB_STAMPS", "-DHB_STAMPS_POTRF", "-o", so,
                        os.path.join(ROOT, "hyperbo_b200/csrc/hb_capi.cu")])
 lib = ctypes.CDLL(so)
 h = ctypes.c_void_p()
