@@ -345,7 +345,18 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
                         const void* raw, uint64_t warp_mask, void* sums_out,
                         void* nll_task_out, int32_t* info_out, void* stream) {
   HB_DISPATCH(nll_grad_batched_impl, h, kernel_id, mean_id, T, offs, d, X, y,
-              raw, warp_mask, sums_out, nll_task_out, info_out, stream);
+              raw, warp_mask, nullptr, hb::JITTER, sums_out, nll_task_out,
+              info_out, stream);
+}
+
+int hb_nll_grad_weighted(hb_handle_t h, int kernel_id, int mean_id, int T,
+                         const int64_t* offs, int d, const void* X,
+                         const void* y, const void* raw, uint64_t warp_mask,
+                         const void* task_weight, double jitter, void* sums_out,
+                         void* nll_task_out, int32_t* info_out, void* stream) {
+  HB_DISPATCH(nll_grad_batched_impl, h, kernel_id, mean_id, T, offs, d, X, y,
+              raw, warp_mask, task_weight, jitter, sums_out, nll_task_out,
+              info_out, stream);
 }
 
 int hb_adam_step(hb_handle_t h, int P_, void* raw, void* m, void* v,

@@ -162,6 +162,7 @@ __device__ __forceinline__ int mn_off(int blk8, int kl, int g, int t) {
 constexpr int TH_CONST = 0, TH_SV = 1, TH_NV = 2, TH_LS = 3;
 constexpr int TH_INVLS = TH_LS + MAX_DIM;            // 35
 constexpr int TH_CHAIN = TH_INVLS + MAX_DIM;         // 67 (3 + MAX_DIM entries)
+constexpr int TH_DIAG = 110;  // noise_variance + jitter (what is added to diag K)
 constexpr int TH_SIZE = 128;
 constexpr double JITTER = 1e-6;    // basics/linalg.py:42
 constexpr double EPS_WARP = 1e-10; // gp_utils/utils.py:28,73

@@ -97,6 +97,19 @@ PYBIND11_MODULE(_C, m) {
                          P(nll_task), (int32_t*)P(info), P(stream)),
                      "hb_nll_grad_batched");
            })
+      .def("nll_grad_weighted",
+           [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
+              int d, ptr_t X, ptr_t y, ptr_t raw, uint64_t mask, ptr_t weight,
+              double jitter, ptr_t sums, ptr_t nll_task, ptr_t info,
+              ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_nll_grad_weighted(
+                         s.h, kernel_id, mean_id, (int)offs.size() - 1,
+                         offs.data(), d, P(X), P(y), P(raw), mask, P(weight),
+                         jitter, P(sums), P(nll_task), (int32_t*)P(info),
+                         P(stream)),
+                     "hb_nll_grad_weighted");
+           })
       .def("adam_step",
            [](Handle& s, int np, ptr_t raw, ptr_t mm, ptr_t vv, ptr_t accepted,
               ptr_t sums, ptr_t scal, double lr, double b1, double b2, double eps,

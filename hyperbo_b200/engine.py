@@ -199,8 +199,11 @@ class Engine:
 
   def nll_grad(self, kernel_id: int, mean_id: int, ds: PackedDataset, raw,
                mask: int, sums_out: Optional[torch.Tensor] = None,
-               want_task_nll=False):
-    """-> sums (P+2,) = [sum nll, sum d/d raw_p ..., count] (+ per-task nll)."""
+               want_task_nll=False, weights: Optional[torch.Tensor] = None,
+               jitter: Optional[float] = None):
+    """-> sums (P+2,) = [sum w nll, sum w d/d raw_p ..., count] (+ per-task
+    nll).  `weights` (T,) and `jitter` select hb_nll_grad_weighted (the building
+    block of the KL objectives); without them it is hb_nll_grad_batched."""
     raw = self.tensor(raw)
     P = 3 + ds.d
     if sums_out is None:
@@ -208,6 +211,19 @@ class Engine:
     T = ds.num_tasks
     nll_task = torch.zeros((max(T, 1),), device=self.device,
                            dtype=self.dtype) if want_task_nll else None
+    if weights is not None or jitter is not None:
+      if weights is not None:
+        weights = self.tensor(weights).reshape(-1)
+        if weights.shape[0] != T:
+          raise ValueError(f"weights has {weights.shape[0]} entries for {T} tasks")
+      self.h.nll_grad_weighted(
+          kernel_id, mean_id, ds.offs, ds.d, ds.x.data_ptr(), ds.y.data_ptr(),
+          raw.data_ptr(), mask, weights.data_ptr() if weights is not None else 0,
+          JITTER if jitter is None else float(jitter), sums_out.data_ptr(),
+          nll_task.data_ptr() if want_task_nll else 0, 0, self._stream())
+      if want_task_nll:
+        return sums_out, nll_task[:T]
+      return sums_out
     self.h.nll_grad_batched(
         kernel_id, mean_id, ds.offs, ds.d, ds.x.data_ptr(), ds.y.data_ptr(),
         raw.data_ptr(), mask, sums_out.data_ptr(),

@@ -5,9 +5,10 @@ with the per-task hot path running in the B200 engine.
 Differences forced by the platform (documented in DESIGN.md):
   * arrays are torch CUDA float64 tensors; `key` arguments are int seeds or
     torch.Generators (jax.random does not exist here);
-  * the objective must be the NLL (callable `objectives.nll` /
-    `objectives.neg_log_marginal_likelihood` or the strings 'nll' /
-    'neg_log_marginal_likelihood'); method must be 'adam'.
+  * the objective must be built from this package's objectives (nll, kl / ekl /
+    regkl and their add / mul combinations, or their names as strings): the
+    engine differentiates them in closed form and cannot trace arbitrary
+    Python callables.
 """
 from __future__ import annotations
 
@@ -36,8 +37,9 @@ GPParams = defs.GPParams
 
 
 def _is_nll(objective) -> bool:
-  return objective in (obj.neg_log_marginal_likelihood, obj.nll, "nll",
-                       "neg_log_marginal_likelihood")
+  """True for the plain NLL (the fast path: hb_nll_grad_batched on one packed
+  batch); other objectives run as an objectives.ObjectiveProgram."""
+  return obj.objective_terms(objective) == [(1.0, "nll", {})]
 
 
 def _dist_world():
@@ -79,11 +81,16 @@ class AdamTrainer:
     self._nsteps = 0
 
   def _enqueue(self, ds):
-    self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
-                      sums_out=self.sums)
-    if self.allreduce:
-      import torch.distributed as dist
-      dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)
+    if isinstance(ds, obj.ObjectiveProgram):
+      # general objective (nll + c * kl, ...): its launches, scaling and
+      # all-reduce are the program's; sums = [value, gradient, 1]
+      ds.sums(self.raw, self.mask, out=self.sums)
+    else:
+      self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
+                        sums_out=self.sums)
+      if self.allreduce:
+        import torch.distributed as dist
+        dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)
     self.eng.adam_step(self.P, self.raw, self.m, self.v, self.accepted,
                        self.sums, self.scal, self.lr, self.b1, self.b2,
                        self.eps, self.tie_lengthscale)
@@ -231,10 +238,13 @@ def _infer_parameters_quasi_newton(eng, kid, mid, params, dataset, warp_func,
                 ([raw0[3]] if scalar_ls else list(raw0[3:])))
 
   def val_and_grad(v):
-    sums = eng.nll_grad(kid, mid, ds, to_raw(v), mask)
-    if world > 1:
-      import torch.distributed as dist
-      dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    if isinstance(ds, obj.ObjectiveProgram):
+      sums = ds.sums(to_raw(v), mask)
+    else:
+      sums = eng.nll_grad(kid, mid, ds, to_raw(v), mask)
+      if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     s = sums.cpu().numpy()
     cnt = max(s[-1], 1.0)
     return float(s[0] / cnt), from_raw_grad(s[1:-1] / cnt)
@@ -288,10 +298,8 @@ def infer_parameters(mean_func,
     return init_params
   if method not in ("adam", "lbfgs", "bfgs"):
     raise ValueError(f"Optimization method {method} is not supported.")
-  if not _is_nll(objective):
-    raise NotImplementedError(
-        "the engine trains with objective = neg_log_marginal_likelihood only")
-  if "priors" in params.config:
+  plain_nll = _is_nll(objective)  # raises for objectives the engine cannot
+  if "priors" in params.config:    # differentiate
     raise NotImplementedError("log-prior terms (objectives.py:197-207)")
 
   kid = _kernel.kernel_id_of(cov_func)
@@ -300,6 +308,13 @@ def infer_parameters(mean_func,
   rank, world = _dist_world()
 
   def pack(batch):
+    if not plain_nll:
+      prog = obj.compile_objective(objective, mean_func, cov_func, batch, rank,
+                                   world)
+      if not prog.has_exact_grad:
+        raise NotImplementedError(
+            "kl_multivariate_normal with eps > 0 is value-only on the engine")
+      return prog
     items = obj._select(batch, exclude_aligned=True)  # pylint: disable=protected-access
     return eng.pack(shard_tasks(items, rank, world))
 
@@ -364,10 +379,13 @@ def infer_parameters(mean_func,
     final = trainer.accepted
     if not trainer.stopped:
       # gp.py:147-150: evaluate the last update once more, accept iff finite
-      sums = eng.nll_grad(kid, mid, ds, trainer.raw, mask)
-      if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+      if plain_nll:
+        sums = eng.nll_grad(kid, mid, ds, trainer.raw, mask)
+        if world > 1:
+          import torch.distributed as dist
+          dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+      else:
+        sums = ds.sums(trainer.raw, mask)
       if math.isfinite(float(sums[0] / sums[-1])):
         final = trainer.raw
     params.model = to_model(final)
@@ -552,10 +570,11 @@ class GP:
     logging.info(msg=f"params = {self.params}")
     return self.params
 
-  def neg_log_marginal_likelihood(self):
+  def neg_log_marginal_likelihood(self, use_cholesky=True):
     """Total nll and dict key -> nll (gp.py:487-497).  The reference evaluates
-    this with its SVD branch; the engine uses the Cholesky branch, which the
-    reference's own test pins to agree (objectives_test.py:298-301)."""
+    this with its SVD branch (use_cholesky=False: Gram matrix from the engine,
+    SVD from cuSOLVER); the default here is the engine's Cholesky branch, which
+    the reference's own test pins to agree (objectives_test.py:298-301)."""
     return obj.neg_log_marginal_likelihood(
         mean_func=self.mean_func,
         cov_func=self.cov_func,
@@ -563,12 +582,36 @@ class GP:
         dataset=self.dataset,
         warp_func=self.warp_func,
         return_key2nll=True,
-        use_cholesky=True)
+        use_cholesky=use_cholesky)
+
+  def empirical_divergence(self, distance=obj._utils.kl_multivariate_normal):
+    """Empirical divergence from sample mean / covariance (gp.py:499-509)."""
+    return obj.multivariate_normal_divergence(
+        mean_func=self.mean_func,
+        cov_func=self.cov_func,
+        params=self.params,
+        dataset=self.dataset,
+        warp_func=self.warp_func,
+        distance=distance)
 
   def stats(self, verbose=True):
-    raise NotImplementedError(
-        "GP.stats() needs the EKL / Euclidean objectives (gp.py:511-533), a "
-        "'next' row of the scope table; use neg_log_marginal_likelihood()")
+    """Objective stats of the current model (gp.py:511-533):
+    (nll, ekl, ekl_partial, euc, key2nll)."""
+    import functools
+    nll, key2nll = self.neg_log_marginal_likelihood(use_cholesky=False)
+    kl = obj._utils.kl_multivariate_normal
+    ekl = self.empirical_divergence(
+        distance=functools.partial(kl, eps=1e-6, partial=False))
+    ekl_partial = self.empirical_divergence(
+        distance=functools.partial(kl, eps=1e-6, partial=True))
+    euc = self.empirical_divergence(
+        distance=obj._utils.euclidean_multivariate_normal)
+    nll, ekl, ekl_partial, euc = (float(v) for v in (nll, ekl, ekl_partial, euc))
+    msg = f"nll = {nll}, ekl = {ekl}, ekl_partial = {ekl_partial}, euc = {euc}"
+    if verbose:
+      print(msg)
+    logging.info(msg=msg)
+    return nll, ekl, ekl_partial, euc, {k: float(v) for k, v in key2nll.items()}
 
   # ---- prediction (gp.py:540-620) ----------------------------------------
   def setup_predictor(self, sub_dataset_key=0):

@@ -1,9 +1,15 @@
-"""Objective functions -- mirrors hyperbo/gp_utils/objectives.py:109-210
-(neg_log_marginal_likelihood, Cholesky branch) on the engine, plus the
-value-and-gradient entry that replaces jax.value_and_grad (gp.py:134)."""
+"""Objective functions -- mirrors hyperbo/gp_utils/objectives.py on the engine:
+neg_log_marginal_likelihood (:109-210; Cholesky branch on the hot path, SVD
+branch through cuSOLVER), multivariate_normal_divergence (:29-101; the
+empirical-KL objective on aligned data, evaluated -- gradient included -- by
+the same batched factorisation kernels), the add / mul combinators (:221-247),
+and the value-and-gradient entry that replaces jax.value_and_grad (gp.py:134).
+"""
 from __future__ import annotations
 
-from typing import Dict, Tuple
+import functools
+import math
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -11,6 +17,7 @@ from hyperbo_b200 import engine as _engine
 from hyperbo_b200.basics import params_utils
 from hyperbo_b200.gp_utils import kernel as _kernel
 from hyperbo_b200.gp_utils import mean as _mean
+from hyperbo_b200.gp_utils import utils as _utils
 
 retrieve_params = params_utils.retrieve_params
 
@@ -49,9 +56,8 @@ def neg_log_marginal_likelihood(mean_func, cov_func, params, dataset,
   """Negative log marginal likelihood of a (multi-task) GP, averaged over the
   non-empty, non-aligned sub-datasets (objectives.py:109-210)."""
   if not use_cholesky:
-    raise NotImplementedError(
-        "the SVD branch (objectives.py:157-176) is not on the engine's hot "
-        "path; use use_cholesky=True")
+    return _nll_svd(mean_func, cov_func, params, dataset, warp_func,
+                    exclude_aligned, return_key2nll)
   if "priors" in params.config:
     raise NotImplementedError("log-prior terms (objectives.py:197-207)")
   eng, kid, mid, ds, raw, mask = _prepare(mean_func, cov_func, params, dataset,
@@ -86,22 +92,308 @@ def nll_value_and_grad(mean_func, cov_func, params, dataset, warp_func=None,
   return sums[0] / cnt, grads
 
 
+def _nll_svd(mean_func, cov_func, params, dataset, warp_func, exclude_aligned,
+             return_key2nll):
+  """The SVD branch (objectives.py:157-176; what GP.stats() prints): the
+  covariance comes from the engine's Gram kernel, the decomposition from
+  cuSOLVER (a plain library call: this branch is diagnostics, not the hot
+  path)."""
+  from hyperbo_b200.basics import linalg as _linalg
+  total, key2nll, num = None, {}, 0
+  for k, x, y in _select(dataset, exclude_aligned):
+    vy, cov = _linalg.compute_delta_y_and_cov(mean_func, cov_func, params, x, y,
+                                              warp_func)
+    u, sg, vh = torch.linalg.svd(cov)
+    kinvy = vh.T @ ((u.T @ vy) / sg[:, None])
+    val = 0.5 * torch.sum(vy.T @ kinvy + torch.sum(torch.log(sg)) +
+                          x.shape[0] * math.log(2 * math.pi))
+    key2nll[k] = val
+    total = val if total is None else total + val
+    num += 1
+  if num == 0:
+    eng = _engine.Engine.get()
+    total = torch.zeros((), device=eng.device, dtype=eng.dtype)
+  else:
+    total = total / num
+  return (total, key2nll) if return_key2nll else total
+
+
 nll = neg_log_marginal_likelihood
 
 
-def _unsupported(name):
+# ---------------------------------------------------------------------------
+# Objectives as engine programs.
+#
+# Every trainable objective here is a weighted sum of per-task NLL values, so
+# one kernel sequence (hb_nll_grad_weighted) serves them all:
+#   nll  : mean over the non-aligned tasks                 (objectives.py:178-195)
+#   kl   : per aligned sub-dataset (x (n,d), y (n,m)), with mu0 = mean_q y,
+#          Yc = (y - mu0)/sqrt(m), K1 = K + (noise + eps) I, dvec = m(x) - mu0:
+#            tr(K1^-1 cov0) + dvec'K1^-1 dvec + logdet K1     (utils.py:84-106)
+#          = 2 sum_q nll0(Yc_q) + 2 nll_m(mu0) - 2 m nll0(0) - n log 2pi
+#          where nll0 / nll_m are the per-task NLL with zero / the model's mean
+#          function and jitter = eps:  m + 2 tasks that share x.  The gradient
+#          is the same weighted sum of the per-task gradients.
+# ---------------------------------------------------------------------------
+class _Launch:
+  """One weighted engine call: value/grad sums are scaled by `scale`."""
 
-  def f(*args, **kwargs):
+  def __init__(self, ds, mean_id, weights, jitter, scale):
+    self.ds, self.mean_id, self.weights = ds, mean_id, weights
+    self.jitter, self.scale = jitter, scale
+
+
+class ObjectiveProgram:
+  """An objective compiled against a dataset: `sums(raw, mask)` enqueues its
+  launches and returns a device vector [value, d value/d raw_p ..., 1] (the
+  layout hb_adam_step consumes).  With torch.distributed initialised the tasks
+  of every launch are sharded round-robin and ONE all-reduce combines the
+  ranks' partial vectors."""
+
+  def __init__(self, eng, kid, d, launches: List[_Launch], const: float,
+               world: int, trace_terms=()):
+    self.eng, self.kid, self.d = eng, kid, d
+    self.P = 3 + d
+    self.launches = [l for l in launches if l.ds.num_tasks > 0]
+    self.const = float(const)
+    self.world = world
+    # (scale, ds): value-only  scale * eps * tr(K1^-1)  terms of kl with eps > 0
+    self.trace_terms = [t for t in trace_terms if t[1].num_tasks > 0]
+    self.has_exact_grad = not trace_terms
+
+  def sums(self, raw, mask, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    eng = self.eng
+    raw = eng.tensor(raw)
+    if out is None:
+      out = torch.empty(self.P + 2, device=eng.device, dtype=eng.dtype)
+    out.zero_()
+    for l in self.launches:
+      s = eng.nll_grad(self.kid, l.mean_id, l.ds, raw, mask, weights=l.weights,
+                       jitter=l.jitter)
+      out[:self.P + 1].add_(s[:self.P + 1], alpha=l.scale)
+    for scale, ds, eps in self.trace_terms:
+      # tr(K1^-1) = 2 d nll0(0)/d noise_variance (un-chained)
+      s = eng.nll_grad(self.kid, 0, ds, raw, mask, jitter=eps)
+      chain = torch.sigmoid(raw[2]) if (mask >> 2) & 1 else 1.0
+      out[0] += scale * eps * 2.0 * s[3] / chain
+    if self.world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    out[0] += self.const
+    out[self.P + 1] = 1.0
+    return out
+
+
+def objective_terms(objective) -> List[Tuple[float, str, dict]]:
+  """Decompose an objective callable into [(coefficient, kind, kwargs)] with
+  kind in {'nll', 'kl', 'euc'}; raises NotImplementedError for callables that
+  were not built from this module's objectives / combinators."""
+  if isinstance(objective, str):
+    if objective not in globals():
+      raise NotImplementedError(f"unknown objective '{objective}'")
+    objective = globals()[objective]
+  terms = getattr(objective, "_hb_terms", None)
+  if terms is not None:
+    return list(terms)
+  kw = {}
+  f = objective
+  while isinstance(f, functools.partial):
+    kw = {**f.keywords, **kw}
+    f = f.func
+  if f is neg_log_marginal_likelihood:
+    return [(1.0, "nll", {})]
+  if f is multivariate_normal_divergence:
+    kind, dkw = _utils.distance_spec(
+        kw.get("distance", _utils.kl_multivariate_normal))
+    return [(1.0, kind, dkw)]
+  raise NotImplementedError(
+      "the engine differentiates objectives in closed form: the objective must "
+      "be built from hyperbo_b200.gp_utils.objectives.{nll, kl, ekl, euc, add, "
+      "mul, ...}")
+
+
+def _aligned_subs(dataset):
+  """Sub-dataset filter of objectives.py:86-98."""
+  out = []
+  for k, s in dataset.items():
+    aligned = s[2] if len(s) > 2 else None
+    if aligned is None:
+      continue
+    x, y = torch.as_tensor(s[0]), torch.as_tensor(s[1])
+    if x.shape[0] == 0:
+      continue
+    if y.dim() != 2 or y.shape[1] == 0 or y.shape[0] != x.shape[0]:
+      raise ValueError(f"dataset[{k}].x has shape {tuple(x.shape)} but "
+                       f"dataset[{k}].y has shape {tuple(y.shape)}")
+    out.append((k, x, y))
+  return out
+
+
+def _shard(items, rank, world):
+  return [it for t, it in enumerate(items) if t % world == rank]
+
+
+def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
+                      ) -> ObjectiveProgram:
+  """Build the engine program of `objective` on `dataset` (this rank's share)."""
+  kid = _kernel.kernel_id_of(cov_func)
+  mid = _mean.mean_id_of(mean_func)
+  eng = _engine.Engine.get()
+  launches, const, trace_terms, d = [], 0.0, [], None
+
+  def pack_weighted(tasks, mean_id, jitter):
+    """tasks: [(x, y, w)] -> launch with per-task weights (scale 1)."""
+    mine = _shard(tasks, rank, world)
+    ds = eng.pack([(i, x, y) for i, (x, y, _) in enumerate(mine)])
+    if ds.num_tasks == 0:
+      return
+    wts = eng.tensor([w for _, _, w in mine])
+    launches.append(_Launch(ds, mean_id, wts, jitter, 1.0))
+
+  for coef, kind, kw in objective_terms(objective):
+    if kind == "nll":
+      items = _select(dataset, exclude_aligned=True)
+      if not items:
+        continue
+      ds = eng.pack(_shard(items, rank, world))
+      launches.append(_Launch(ds, mid, None, None, coef / len(items)))
+      d = d or int(torch.as_tensor(items[0][1]).shape[1])
+    elif kind == "kl":
+      if not kw.get("partial", True):
+        raise NotImplementedError(
+            "kl_multivariate_normal(partial=False) is a whitened diagnostic "
+            "(GP.stats); it has no engine program / gradient")
+      eps = float(kw.get("eps", 0.0))
+      subs = _aligned_subs(dataset)
+      if not subs:
+        continue
+      c = coef * float(kw.get("weight", 1.0)) / len(subs)
+      zero_mean_tasks, model_mean_tasks, zero_tasks = [], [], []
+      for _, x, y in subs:
+        x, y = eng.tensor(x), eng.tensor(y)
+        n, m = y.shape
+        d = d or int(x.shape[1])
+        mu0 = y.mean(dim=1)
+        yc = (y - mu0[:, None]) / math.sqrt(m)
+        for q in range(m):
+          zero_mean_tasks.append((x, yc[:, q], 2.0 * c))
+        zeros = torch.zeros_like(mu0)
+        zero_mean_tasks.append((x, zeros, -2.0 * m * c))
+        model_mean_tasks.append((x, mu0, 2.0 * c))
+        zero_tasks.append((x, zeros, 1.0))
+        const -= c * n * math.log(2 * math.pi)
+      if mid == 0:
+        zero_mean_tasks += model_mean_tasks
+        model_mean_tasks = []
+      pack_weighted(zero_mean_tasks, 0, eps)
+      pack_weighted(model_mean_tasks, mid, eps)
+      if eps > 0.0:
+        mine = _shard(zero_tasks, rank, world)
+        trace_terms.append((c, eng.pack([(i, x, y) for i, (x, y, _) in
+                                         enumerate(mine)]), eps))
+    else:
+      raise NotImplementedError(
+          "the Euclidean regulariser (objectives.py:104-106) is value-only "
+          "here (GP.stats); it has no engine program / gradient")
+  if rank != 0:
+    const = 0.0  # added once: the partial vectors are summed over ranks
+  return ObjectiveProgram(eng, kid, d or 1, launches, const, world, trace_terms)
+
+
+def multivariate_normal_divergence(mean_func, cov_func, params, dataset,
+                                   warp_func=None,
+                                   distance=_utils.kl_multivariate_normal):
+  """Divergence between N(sample mean, sample cov) of every ALIGNED sub-dataset
+  and the GP's N(m(x), K(x,x) + noise I), averaged over those sub-datasets
+  (objectives.py:29-101).  The partial KL runs on the factorisation kernels;
+  the whitened KL (partial=False) and the Euclidean distance are value-only
+  diagnostics assembled from the engine's Gram matrix with cuSOLVER."""
+  kind, kw = _utils.distance_spec(distance)
+  eng = _engine.Engine.get()
+  subs = _aligned_subs(dataset)
+  if not subs:
+    return torch.zeros((), device=eng.device, dtype=eng.dtype)
+  kid = _kernel.kernel_id_of(cov_func)
+  mid = _mean.mean_id_of(mean_func)
+  d = int(subs[0][1].shape[1])
+  raw, mask, _ = params_utils.pack_raw(params.model, d, mid == 1, warp_func)
+  if kind == "kl" and kw.get("partial", True):
+    prog = compile_objective(
+        functools.partial(multivariate_normal_divergence, distance=distance),
+        mean_func, cov_func, dataset)
+    return prog.sums(raw, mask)[0]
+  total = None
+  for _, x, y in subs:
+    x, y = eng.tensor(x), eng.tensor(y)
+    mu0 = y.mean(dim=1)
+    yc = y - mu0[:, None]
+    cov0 = yc @ yc.T / y.shape[1]
+    mu1 = mean_func(params, x, warp_func=warp_func).to(eng.device).reshape(-1)
+    cov1 = eng.kernel_matrix(kid, x, None, raw, mask, add_noise=True,
+                             jitter=0.0)
+    f = _utils.kl_multivariate_normal if kind == "kl" else \
+        _utils.euclidean_multivariate_normal
+    val = f(mu0=mu0, cov0=cov0, mu1=mu1, cov1=cov1, **kw)
+    total = val if total is None else total + val
+  return total / len(subs)
+
+
+multivariate_normal_euc_distance = functools.partial(
+    multivariate_normal_divergence,
+    distance=_utils.euclidean_multivariate_normal)
+
+kl = multivariate_normal_divergence
+ekl = kl
+euc = multivariate_normal_euc_distance
+regkl = kl
+regeuc = euc
+
+
+def add(*objectives):
+  """objectives.py:221-227."""
+
+  def added_objective(*args, **kwargs):
+    return sum([o(*args, **kwargs) for o in objectives])
+
+  added_objective._hb_terms = [t for o in objectives for t in objective_terms(o)]
+  return added_objective
+
+
+def mul(c, objective):
+  """objectives.py:230-236."""
+
+  def multiplied_objective(*args, **kwargs):
+    return c * objective(*args, **kwargs)
+
+  multiplied_objective._hb_terms = [(c * co, kind, kw)
+                                    for co, kind, kw in objective_terms(objective)]
+  return multiplied_objective
+
+
+# objectives.py:239-247 (nll_regeuc01 / nll_regeuc10 are built from regkl there
+# too -- reproduced as is)
+nll_regkl = lambda c: add(nll, mul(c, regkl))
+nll_regeuc = lambda c: add(nll, mul(c, regeuc))
+nll_regkl1 = nll_regkl(1.)
+nll_regeuc1 = nll_regeuc(1.)
+nll_regkl01 = nll_regkl(.1)
+nll_regeuc01 = nll_regkl(.1)
+nll_regkl10 = nll_regkl(10.)
+nll_regeuc10 = nll_regkl(10.)
+
+
+def value_and_grad(objective, mean_func, cov_func, params, dataset,
+                   warp_func=None) -> Tuple[torch.Tensor, Dict]:
+  """(objective value, d value / d params.model) for any objective built from
+  nll / kl / add / mul -- what jax.value_and_grad(loss_func) yields at
+  gp.py:134."""
+  prog = compile_objective(objective, mean_func, cov_func, dataset)
+  if not prog.has_exact_grad:
     raise NotImplementedError(
-        f"objective '{name}' (EKL / Euclidean regulariser on aligned data, "
-        "objectives.py:29-101) is outside the B200 hot path")
-
-  f.__name__ = name
-  return f
-
-
-multivariate_normal_divergence = _unsupported("multivariate_normal_divergence")
-multivariate_normal_euc_distance = _unsupported(
-    "multivariate_normal_euc_distance")
-kl = ekl = regkl = multivariate_normal_divergence
-euc = regeuc = multivariate_normal_euc_distance
+        "kl_multivariate_normal with eps > 0 is value-only on the engine")
+  mid = _mean.mean_id_of(mean_func)
+  raw, mask, _ = params_utils.pack_raw(params.model, prog.d, mid == 1, warp_func)
+  sums = prog.sums(raw, mask)
+  grads = params_utils.unpack_like(params.model, sums[1:-1], prog.d, mid == 1,
+                                   is_grad=True)
+  return sums[0], grads

@@ -134,6 +134,29 @@ int hb_nll_grad_batched(hb_handle_t h, int kernel_id, int mean_id, int T,
                         void* sums_out, void* nll_task_out_or_null,
                         int32_t* info_out_or_null, void* stream);
 
+/* Same launch sequence with two generalisations, which turn it into the
+ * building block of the reference's OTHER training objective, the empirical KL
+ * divergence on aligned data (objectives.multivariate_normal_divergence,
+ * gp_utils/objectives.py:29-101, with utils.kl_multivariate_normal /
+ * partial_kl_mvn, gp_utils/utils.py:84-141):
+ *   task_weight_or_null : (T,) device scalars w_t; sums_out[0] = sum w_t nll_t,
+ *                         sums_out[1+p] = sum w_t d nll_t / d raw_p
+ *                         (sums_out[1+P] stays the unweighted task count);
+ *   jitter              : what is added to the diagonal next to the noise
+ *                         variance (1e-6 in linalg.py:42; `eps`, default 0, in
+ *                         utils.kl_multivariate_normal).
+ * With B = [Yc / sqrt(m) | mu_model - mu_data] (n x (m+1)) the partial KL is
+ *   tr(K1^-1 S0) + d'K1^-1 d + logdet K1 = 2 sum_q nll(y = B_q) - 2 m nll(y = 0)
+ *                                          - n log 2pi,
+ * i.e. ONE weighted call over m+2 tasks that share X (hyperbo_b200/gp_utils/
+ * objectives.py builds them), gradient included. */
+int hb_nll_grad_weighted(hb_handle_t h, int kernel_id, int mean_id, int T,
+                         const int64_t* offs_host, int d, const void* X,
+                         const void* y, const void* raw, uint64_t warp_mask,
+                         const void* task_weight_or_null, double jitter,
+                         void* sums_out, void* nll_task_out_or_null,
+                         int32_t* info_out_or_null, void* stream);
+
 /* ---- a11: one optax.adam update (gp_utils/gp.py:124,143-144) ------------ */
 /* state (device, handle dtype): raw[P], m[P], v[P], accepted[P].
  * scalars_io (device, 4 scalars): [0] loss of this step (written),

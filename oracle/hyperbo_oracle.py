@@ -300,6 +300,155 @@ def nll_value_and_grad(mean_name, cov_name, model, dataset, warp_func=None):
 
 
 # ----------------------------------------------------------------------------
+# divergence objectives on ALIGNED sub-datasets
+# gp_utils/objectives.py:29-101, gp_utils/utils.py:84-173
+# ----------------------------------------------------------------------------
+def svd_matrix_sqrt(cov):
+  """basics/linalg.py:112-126: A with A A' = cov, full column rank."""
+  u, s, _ = np.linalg.svd(cov)
+  factor = u * np.sqrt(s[..., None, :])
+  tol = s.max() * np.finfo(s.dtype).eps / 2.0 * np.sqrt(2 * cov.shape[0] + 1.0)
+  rank = int(np.count_nonzero(s > tol))
+  return factor[:, :rank]
+
+
+def partial_kl_mvn(mu0, cov0, mu1, cov1):
+  """utils.py:84-106: tr(cov1^-1 cov0) + (mu1-mu0)' cov1^-1 (mu1-mu0) + logdet cov1."""
+  mu_diff = mu1 - mu0
+  chol1 = np.linalg.cholesky(cov1)
+  cov1invmudiff = spla.cho_solve((chol1, True), mu_diff)
+  trcov1invcov0 = float(np.trace(spla.cho_solve((chol1, True), cov0)))
+  mahalanobis = float(np.dot(mu_diff, cov1invmudiff))
+  logdetcov1 = float(np.sum(2 * np.log(np.diag(chol1))))
+  return trcov1invcov0 + mahalanobis + logdetcov1
+
+
+def kl_multivariate_normal(mu0, cov0, mu1, cov1, weight=1.0, eps=0.0,
+                           partial=True):
+  """utils.py:109-148."""
+  cov0 = np.atleast_2d(np.asarray(cov0, dtype=np.float64))
+  cov1 = np.atleast_2d(np.asarray(cov1, dtype=np.float64))
+  if eps > 0.0:
+    cov0 = cov0 + np.eye(cov0.shape[0]) * eps
+    cov1 = cov1 + np.eye(cov1.shape[0]) * eps
+  if partial:
+    return weight * partial_kl_mvn(mu0, cov0, mu1, cov1)
+  chol0 = svd_matrix_sqrt(cov0)
+  chol0inv = np.linalg.pinv(chol0)
+  mu1 = chol0inv @ (mu1 - mu0)
+  cov1 = chol0inv @ cov1 @ chol0inv.T
+  mu0 = np.zeros_like(mu1)
+  cov0 = np.eye(cov1.shape[0])
+  return weight * 0.5 * (partial_kl_mvn(mu0, cov0, mu1, cov1) - chol0.shape[1])
+
+
+def euclidean_multivariate_normal(mu0, cov0, mu1, cov1, mean_weight=1.0,
+                                  cov_weight=1.0, **unused):
+  """utils.py:151-173 (safe_l2norm = plain l2 norm in the forward pass)."""
+  mean_diff = math.sqrt(float(np.sum((mu0 - mu1)**2)))
+  cov_diff = math.sqrt(float(np.sum((np.atleast_2d(cov0) - cov1)**2)))
+  return mean_weight * mean_diff + cov_weight * cov_diff
+
+
+def _data_moments(y):
+  """objectives.py:69-70: sample mean / biased sample covariance over the m
+  columns of an aligned y (n, m)."""
+  y = np.asarray(y, dtype=np.float64)
+  mu = np.mean(y, axis=1)
+  yc = y - mu[:, None]
+  return mu, (yc @ yc.T) / y.shape[1]
+
+
+def multivariate_normal_divergence(mean_name, cov_name, model, dataset,
+                                   warp_func=None,
+                                   distance=kl_multivariate_normal):
+  """objectives.py:29-101: mean over the non-empty ALIGNED sub-datasets of
+  distance(N(data mean, data cov), N(m(x), K(x,x) + noise I))."""
+  total, num = 0.0, 0
+  for k, s in dataset.items():
+    x, y = np.asarray(s[0], dtype=np.float64), np.asarray(s[1], dtype=np.float64)
+    aligned = s[2] if len(s) > 2 else None
+    if aligned is None or x.shape[0] == 0:
+      continue
+    if y.shape[1] == 0 or y.shape[0] != x.shape[0]:
+      raise ValueError(f"dataset[{k}].x has shape {x.shape} but "
+                       f"dataset[{k}].y has shape {y.shape}")
+    mu_data, cov_data = _data_moments(y)
+    mu_model = mean_vector(mean_name, model, x, warp_func).flatten()
+    (nv,) = retrieve_params(model, ["noise_variance"], warp_func)
+    cov_model = cov_matrix(cov_name, model, x, warp_func=warp_func) + \
+        np.eye(x.shape[0]) * float(np.squeeze(nv))
+    total += distance(mu0=mu_data, cov0=cov_data, mu1=mu_model, cov1=cov_model)
+    num += 1
+  return 0.0 if num == 0 else total / num
+
+
+def kl_value_and_grad(mean_name, cov_name, model, dataset, warp_func=None,
+                      eps=0.0, weight=1.0):
+  """Partial-KL divergence (the `kl` / `ekl` / `regkl` objective) and its
+  gradient w.r.t. the raw parameters in closed form (matrix calculus, not the
+  engine's NLL decomposition): with K1 = K + (nv + eps) I, S = cov0 + eps I +
+  d d', d = mu1 - mu0:   G = K1^-1 - K1^-1 S K1^-1,   d kl/d theta = <G, dK1>,
+  d kl/d constant = 2 sum(K1^-1 d)."""
+  total, num = 0.0, 0
+  gsum: Dict[str, np.ndarray] = {}
+  for _, s in dataset.items():
+    x, y = np.asarray(s[0], dtype=np.float64), np.asarray(s[1], dtype=np.float64)
+    aligned = s[2] if len(s) > 2 else None
+    if aligned is None or x.shape[0] == 0:
+      continue
+    n, d = x.shape
+    mu0, cov0 = _data_moments(y)
+    ls_raw = np.asarray(model["lengthscale"], dtype=np.float64)
+    ls, sv, nv = retrieve_params(
+        model, ["lengthscale", "signal_variance", "noise_variance"], warp_func)
+    ls_full = np.broadcast_to(np.asarray(ls, dtype=np.float64), (d,))
+    sv, nv = float(np.squeeze(sv)), float(np.squeeze(nv))
+    dvec = mean_vector(mean_name, model, x, warp_func).flatten() - mu0
+    r2, diff = _scaled_sqdist(x, x, ls_full)
+    k = _kernel_from_r2(cov_name, r2, sv)
+    k1 = k + np.eye(n) * (nv + eps)
+    chol = np.linalg.cholesky(k1)
+    kinv = spla.cho_solve((chol, True), np.eye(n))
+    smat = cov0 + np.eye(n) * eps + np.outer(dvec, dvec)
+    val = float(np.trace(kinv @ (cov0 + np.eye(n) * eps)) + dvec @ kinv @ dvec +
+                2 * np.sum(np.log(np.diag(chol))))
+    g = kinv - kinv @ smat @ kinv
+    w = _pair_weight(cov_name, r2, k, sv)
+    d_ls = np.einsum("ij,ijk->k", g * w, diff * diff) / ls_full
+    d_sv = float(np.sum(g * k) / sv)
+    d_nv = float(np.trace(g))
+    d_c = 2.0 * float(np.sum(kinv @ dvec)) if mean_name == "constant" else 0.0
+
+    def warped(key):
+      return bool(warp_func) and key in warp_func and \
+          warp_func[key] is not identity_warp
+
+    if warped("lengthscale"):
+      d_ls = d_ls * sigmoid(np.broadcast_to(ls_raw, (d,)))
+    if warped("signal_variance"):
+      d_sv *= float(sigmoid(model["signal_variance"]))
+    if warped("noise_variance"):
+      d_nv *= float(sigmoid(model["noise_variance"]))
+    grad = {
+        "lengthscale": (np.sum(d_ls).reshape(ls_raw.shape) if ls_raw.size == 1
+                        else d_ls.reshape(ls_raw.shape)),
+        "signal_variance": d_sv,
+        "noise_variance": d_nv,
+    }
+    if "constant" in model:
+      grad["constant"] = d_c
+    total += weight * val
+    num += 1
+    for k2, gv in grad.items():
+      gsum[k2] = gsum.get(k2, 0.0) + weight * np.asarray(gv, dtype=np.float64)
+  if num == 0:
+    return 0.0, {k2: np.zeros_like(np.asarray(v, dtype=np.float64))
+                 for k2, v in model.items()}
+  return total / num, {k2: gv / num for k2, gv in gsum.items()}
+
+
+# ----------------------------------------------------------------------------
 # Adam loop  (gp_utils/gp.py:114-157; optax.adam defaults)
 # ----------------------------------------------------------------------------
 class Adam:

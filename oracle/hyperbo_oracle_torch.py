@@ -153,6 +153,69 @@ def neg_log_marginal_likelihood_batched(mean_name, cov_name, model, x, y,
   return torch.mean(nll)
 
 
+def multivariate_normal_divergence(mean_name, cov_name, model, dataset,
+                                   warp_func, eps=0.0, partial=True, euc=False):
+  """objectives.py:29-101 with utils.kl_multivariate_normal (utils.py:84-148) or
+  euclidean_multivariate_normal (utils.py:151-173), op by op (autograd)."""
+  total, num = 0.0, 0
+  for _, s in dataset.items():
+    if len(s) < 3 or s[2] is None or s[0].shape[0] == 0:
+      continue
+    x, y = s[0], s[1]
+    n = x.shape[0]
+    mu0 = torch.mean(y, dim=1)
+    yc = y - mu0[:, None]
+    cov0 = yc @ yc.T / y.shape[1]  # jnp.cov(y, bias=True)
+    if mean_name == "constant":
+      (c,) = retrieve(model, ["constant"], warp_func)
+      mu1 = c * torch.ones(n, dtype=x.dtype)
+    else:
+      mu1 = torch.zeros(n, dtype=x.dtype)
+    (nv,) = retrieve(model, ["noise_variance"], warp_func)
+    cov1 = cov_matrix(cov_name, model, x, None, warp_func) + torch.eye(
+        n, dtype=x.dtype) * nv
+    if euc:
+      val = _SafeSqrt.apply(torch.sum((mu0 - mu1)**2)) + _SafeSqrt.apply(
+          torch.sum((cov0 - cov1)**2))
+    else:
+      if eps > 0:
+        cov0 = cov0 + torch.eye(n, dtype=x.dtype) * eps
+        cov1 = cov1 + torch.eye(n, dtype=x.dtype) * eps
+      if not partial:
+        u, sg, _ = torch.linalg.svd(cov0.detach())
+        tol = sg.max() * torch.finfo(sg.dtype).eps / 2.0 * math.sqrt(2 * n + 1.0)
+        rank = int((sg > tol).sum())
+        chol0 = (u * torch.sqrt(sg)[None, :])[:, :rank]
+        chol0inv = torch.linalg.pinv(chol0)
+        mu1 = chol0inv @ (mu1 - mu0)
+        cov1 = chol0inv @ cov1 @ chol0inv.T
+        mu0 = torch.zeros_like(mu1)
+        cov0 = torch.eye(rank, dtype=x.dtype)
+      mu_diff = mu1 - mu0
+      chol1 = torch.linalg.cholesky(cov1)
+      val = torch.trace(torch.cholesky_solve(cov0, chol1)) + mu_diff @ \
+          torch.cholesky_solve(mu_diff[:, None], chol1)[:, 0] + \
+          torch.sum(2 * torch.log(torch.diagonal(chol1)))
+      if not partial:
+        val = 0.5 * (val - rank)
+    total = total + val
+    num += 1
+  return total / num if num else torch.zeros(())
+
+
+def divergence_value_and_grad(mean_name, cov_name, model_np: Dict, dataset_np,
+                              warp_func=DEFAULT_WARP_FUNC, **kw):
+  model = to_torch_model(model_np, torch.float64)
+  ds = {k: (torch.as_tensor(s[0], dtype=torch.float64), torch.as_tensor(
+      s[1], dtype=torch.float64)) + tuple(s[2:]) for k, s in dataset_np.items()}
+  loss = multivariate_normal_divergence(mean_name, cov_name, model, ds,
+                                        warp_func, **kw)
+  loss.backward()
+  grads = {k: (v.grad.numpy().copy() if v.grad is not None else
+               torch.zeros_like(v).numpy()) for k, v in model.items()}
+  return float(loss.detach()), grads
+
+
 def to_torch_model(model: Dict, dtype=torch.float64, requires_grad=True):
   return {k: torch.tensor(v, dtype=dtype, requires_grad=requires_grad)
           for k, v in model.items()}

@@ -80,8 +80,71 @@ def build(name):
   return out
 
 
+def make_aligned_dataset(seed, d, spec):
+  """Synthetic dataset with ALIGNED sub-datasets (y: n x m, m tasks evaluated on
+  the same inputs -- what the reference's EKL objective consumes) plus
+  ordinary ones.  spec: list of (n, m, aligned_tag_or_None)."""
+  rng = np.random.default_rng(seed)
+  ds = {}
+  for t, (n, m, tag) in enumerate(spec):
+    x = rng.random((n, d))
+    base = np.sin(3.0 * x[:, :1]) + 0.5 * x[:, -1:]
+    y = 0.3 + base + 0.4 * rng.standard_normal((n, m)) * (1 + x[:, :1])
+    ds[t] = (x, y) if tag is None else (x, y, tag)
+  return ds
+
+
+KL_CASES = {
+    # name: (cov, mean, d, spec)
+    "kl_m52_const_d3": ("matern52", "constant", 3,
+                        [(70, 6, 1), (33, 4, "tag"), (40, 1, None), (0, 3, 2)]),
+    "kl_se_zero_d2": ("squared_exponential", "zero", 2,
+                      [(130, 9, True), (20, 1, None)]),
+}
+
+
+def build_kl(name):
+  import functools
+  cov, mean, d, spec = KL_CASES[name]
+  ds = make_aligned_dataset(7 + len(name), d, spec)
+  rng = np.random.default_rng(5)
+  model = O.init_raw_params(d)
+  model["lengthscale"] = rng.normal(0.0, 0.4, d)
+  model["constant"] = 0.2
+  if mean == "zero":
+    del model["constant"]
+  wf = O.DEFAULT_WARP_FUNC
+  val, grad = O.kl_value_and_grad(mean, cov, model, ds, wf)
+  val_t, grad_t = OT.divergence_value_and_grad(mean, cov, model, ds)
+  assert abs(val - val_t) <= 1e-9 * abs(val), (name, val, val_t)
+  for k in grad:
+    a, b = np.asarray(grad[k], dtype=np.float64), np.asarray(grad_t[k])
+    assert np.max(np.abs(a - b)) <= 1e-9 * (np.max(np.abs(b)) + 1e-12), (name, k)
+  kl = O.kl_multivariate_normal
+  out = {
+      "cov": cov, "mean": mean, "d": d, "raw": raw_vec(model, d),
+      "spec_n": np.array([s[0] for s in spec]),
+      "spec_m": np.array([s[1] for s in spec]),
+      "spec_aligned": np.array([s[2] is not None for s in spec]),
+      "kl": val, "kl_grad": grad_vec(grad, d),
+      "kl_eps": O.multivariate_normal_divergence(
+          mean, cov, model, ds, wf, functools.partial(kl, eps=1e-6)),
+      "kl_full": O.multivariate_normal_divergence(
+          mean, cov, model, ds, wf,
+          functools.partial(kl, eps=1e-6, partial=False)),
+      "euc": O.multivariate_normal_divergence(
+          mean, cov, model, ds, wf, O.euclidean_multivariate_normal),
+  }
+  for t in ds:
+    out[f"x{t}"], out[f"y{t}"] = ds[t][0], ds[t][1]
+  return out
+
+
 if __name__ == "__main__":
   os.makedirs(OUT, exist_ok=True)
   for name in CASES:
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **build(name))
+    print("wrote", name)
+  for name in KL_CASES:
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **build_kl(name))
     print("wrote", name)

@@ -7,9 +7,22 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_cases():
-  return sorted(os.path.basename(p)[:-4]
-                for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def golden_cases(kl=False):
+  names = sorted(os.path.basename(p)[:-4]
+                 for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+  return [n for n in names if n.startswith("kl_") == kl]
+
+
+def load_golden_kl(name):
+  """Fixtures of the divergence objectives on aligned data (make_golden.py)."""
+  z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+  g = {k: z[k] for k in z.files}
+  g["cov"], g["mean"], g["d"] = str(g["cov"]), str(g["mean"]), int(g["d"])
+  ds = {}
+  for t, al in enumerate(g["spec_aligned"]):
+    ds[t] = (g[f"x{t}"], g[f"y{t}"], 1) if al else (g[f"x{t}"], g[f"y{t}"])
+  g["dataset"] = ds
+  return g
 
 
 def load_golden(name):

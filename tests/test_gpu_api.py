@@ -174,9 +174,11 @@ def test_objective_api_and_value_and_grad():
   assert set(grads) == set(model)
   for k in g_ref:
     assert H.rel(grads[k], g_ref[k]) < 1e-8
-  with pytest.raises(NotImplementedError):
-    objectives.neg_log_marginal_likelihood(
-        mean.constant, kernel.matern32, params, dataset, WF, use_cholesky=False)
+  # the SVD branch (objectives.py:157-176) agrees with the Cholesky branch
+  # (objectives_test.py:298-301 asserts 2 places; here to conditioning)
+  v_svd = objectives.neg_log_marginal_likelihood(
+      mean.constant, kernel.matern32, params, dataset, WF, use_cholesky=False)
+  assert abs(float(v_svd) - v_ref) < 1e-8 * abs(v_ref)
 
 
 def test_infer_parameters_matches_oracle_adam_loop():

@@ -109,8 +109,20 @@ def test_registries_keep_reference_names():  # const.py:22-50
       f(p, np.zeros((2, 2)))
   with pytest.raises(NotImplementedError):
     mean.linear_mlp(p, np.zeros((2, 2)))
+  # objectives are recognised, not traced (objectives.py:213-247)
+  assert objectives.objective_terms(objectives.nll) == [(1.0, "nll", {})]
+  assert objectives.objective_terms("ekl") == [(1.0, "kl", {})]
+  assert objectives.objective_terms(objectives.nll_regkl01) == [
+      (1.0, "nll", {}), (0.1, "kl", {})]
+  assert objectives.objective_terms(objectives.regeuc) == [(1.0, "euc", {})]
+  assert objectives.objective_terms(
+      objectives.mul(3.0, objectives.nll_regkl10))[1] == (30.0, "kl", {})
+  import functools
+  assert utils.distance_spec(functools.partial(
+      utils.kl_multivariate_normal, eps=1e-6, partial=False)) == (
+          "kl", {"eps": 1e-6, "partial": False})
   with pytest.raises(NotImplementedError):
-    objectives.ekl(None, None, None, None)
+    objectives.objective_terms(lambda *a, **k: 0.0)
 
 
 def test_sub_sample_dataset_iterator():  # data_utils.py:72-100
@@ -171,9 +183,9 @@ def test_infer_parameters_guards():
   with pytest.raises(ValueError):
     gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)})
   params.config["method"] = "adam"
-  with pytest.raises(NotImplementedError):  # only the NLL objective is trained
+  with pytest.raises(NotImplementedError):  # objectives are recognised, not traced
     gp.infer_parameters(mean.constant, kernel.matern32, params, {0: (x, y)},
-                        objective=objectives.ekl)
+                        objective=lambda *a, **k: 0.0)
 
 
 def test_shard_tasks_round_robin():

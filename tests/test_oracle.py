@@ -191,3 +191,86 @@ def test_acquisition_shapes_and_values():  # acfun_test.py:43-72
   # EI >= 0 and EI(mu=target, std) = std * pdf(0)
   assert np.isclose(O.expected_improvement_sub(1.0, 2.0, 1.0),
                     2.0 / math.sqrt(2 * math.pi))
+
+
+# ---- divergence objectives on aligned data -------------
+@pytest.mark.parametrize("name", H.golden_cases(kl=True))
+def test_kl_oracle_matches_golden(name):
+  import functools
+  g = H.load_golden_kl(name)
+  model = H.model_from_raw(g["raw"], g["d"], g["mean"])
+  val, grad = O.kl_value_and_grad(g["mean"], g["cov"], model, g["dataset"], WF)
+  assert abs(val - g["kl"]) <= 1e-12 * abs(g["kl"])
+  assert H.rel(H.grad_vec(grad, g["d"]), g["kl_grad"]) < 1e-10
+  # direct restatement of objectives.py:29-101 == closed form
+  v0 = O.multivariate_normal_divergence(g["mean"], g["cov"], model,
+                                        g["dataset"], WF)
+  assert abs(v0 - val) <= 1e-11 * abs(val)
+  # op-by-op torch restatement incl. the whitened KL and the Euclidean distance
+  vt, gt = OT.divergence_value_and_grad(g["mean"], g["cov"], model, g["dataset"])
+  assert abs(vt - val) <= 1e-11 * abs(val)
+  for k in grad:
+    assert H.rel(grad[k], gt[k]) < 1e-10, k
+  vf, _ = OT.divergence_value_and_grad(g["mean"], g["cov"], model, g["dataset"],
+                                       eps=1e-6, partial=False)
+  assert abs(vf - g["kl_full"]) <= 1e-8 * abs(g["kl_full"])
+  ve, _ = OT.divergence_value_and_grad(g["mean"], g["cov"], model, g["dataset"],
+                                       euc=True)
+  assert abs(ve - g["euc"]) <= 1e-12 * abs(g["euc"])
+
+
+def test_kl_is_a_weighted_sum_of_task_nlls():
+  """The identity the engine's KL program rests on (objectives.py of the
+  package): with B = [Yc/sqrt(m) | mu0], partial KL = 2 sum_q nll0(B_q) +
+  2 nll_mean(mu0) - 2 m nll0(0) - n log 2pi, all with jitter = eps."""
+  rng = np.random.default_rng(3)
+  n, m, d = 45, 5, 2
+  x = rng.random((n, d))
+  y = rng.standard_normal((n, m)) + 2.0 * x[:, :1]
+  model = O.init_raw_params(d)
+  model["constant"] = 0.7
+  for eps in (0.0, 1e-6):
+    def task_nll(mean_name, yy):
+      chol, kinvy, r = O.solve_gp_linear_system(mean_name, "matern32", model, x,
+                                                yy[:, None], WF, eps=eps)
+      return float(0.5 * (r.T @ kinvy).item() + np.sum(np.log(np.diag(chol))) +
+                   0.5 * n * math.log(2 * math.pi))
+    mu0 = y.mean(axis=1)
+    yc = (y - mu0[:, None]) / math.sqrt(m)
+    total = 2 * sum(task_nll("zero", yc[:, q]) for q in range(m)) + \
+        2 * task_nll("constant", mu0) - 2 * m * task_nll("zero", np.zeros(n)) - \
+        n * math.log(2 * math.pi)
+    import functools
+    ref = O.multivariate_normal_divergence(
+        "constant", "matern32", model, {0: (x, y, 1)}, WF,
+        functools.partial(O.kl_multivariate_normal, eps=eps))
+    if eps > 0:  # cov0 + eps I adds eps tr(K1^-1)
+      _, cov1 = O.compute_delta_y_and_cov("constant", "matern32", model, x,
+                                          y[:, :1], WF, eps=eps)
+      total += eps * np.trace(np.linalg.inv(cov1))
+    assert abs(total - ref) < 1e-10 * abs(ref), (eps, total, ref)
+
+
+def test_kl_gradient_finite_differences():
+  ds = {0: (np.random.default_rng(0).random((30, 2)),
+            np.random.default_rng(1).standard_normal((30, 4)), 1)}
+  model = O.init_raw_params(2)
+  model["lengthscale"] = np.array([0.2, -0.1])
+  _, g = O.kl_value_and_grad("constant", "matern52", model, ds, WF)
+  h = 1e-6
+  for key in ("constant", "signal_variance", "noise_variance"):
+    mp, mm = dict(model), dict(model)
+    mp[key], mm[key] = model[key] + h, model[key] - h
+    fd = (O.multivariate_normal_divergence("constant", "matern52", mp, ds, WF) -
+          O.multivariate_normal_divergence("constant", "matern52", mm, ds, WF)
+          ) / (2 * h)
+    assert abs(fd - g[key]) < 1e-5 * max(1.0, abs(fd)), key
+  for k in range(2):
+    mp, mm = dict(model), dict(model)
+    e = np.zeros(2); e[k] = h
+    mp["lengthscale"], mm["lengthscale"] = model["lengthscale"] + e, \
+        model["lengthscale"] - e
+    fd = (O.multivariate_normal_divergence("constant", "matern52", mp, ds, WF) -
+          O.multivariate_normal_divergence("constant", "matern52", mm, ds, WF)
+          ) / (2 * h)
+    assert abs(fd - g["lengthscale"][k]) < 1e-5 * max(1.0, abs(fd)), k
