@@ -117,8 +117,10 @@ enum Major { KMAJOR = 0, MNMAJOR = 1 };
 // (wm = 1) or (wn = 0) warps skip half of a k range, the remaining tensor work
 // stays balanced over the four sub-partitions.
 // acc[fm][fn][e]: rows 32wm + 8fm + g, cols 32wn + 8fn + 2t + e.
+struct FullK {};  // tag: the full-K warp mapping below
 struct WarpPos {
   int warp, lane, wk, q, wm, wn, g, t;
+  bool fullk;
   __device__ __forceinline__ WarpPos() {
     warp = threadIdx.x >> 5;
     lane = threadIdx.x & 31;
@@ -128,6 +130,27 @@ struct WarpPos {
     wn = q & 1;
     g = lane >> 2;
     t = lane & 3;
+    fullk = false;
+  }
+  // Full-K mapping (no split-K exchange, half the accumulator registers): warp
+  // = one 16-row group r4 = 2 wm + wk of one 32-column half wn, over the whole
+  // k range; acc[fi][fn][e] IS own[fi][fn][e] (rows 16 r4 + 8 fi + g, the same
+  // own_row / own_col formulas).  The two warps of a sub-partition (w, w + 4)
+  // take row groups (r4, 3 - r4) and opposite column halves, so triangular
+  // clipping (now at 16-row granularity) stays balanced over the sub-partitions.
+  __device__ __forceinline__ explicit WarpPos(FullK) {
+    warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    const int s = warp & 3, hi = warp >> 2;
+    int r4 = s >> 1;          // sub-partitions 0,1 -> row group 0; 2,3 -> 1
+    wn = s & 1;
+    if (hi) { r4 = 3 - r4; wn = 1 - wn; }
+    wm = r4 >> 1;
+    wk = r4 & 1;
+    q = 2 * wm + wn;
+    g = lane >> 2;
+    t = lane & 3;
+    fullk = true;
   }
 };
 
@@ -143,8 +166,14 @@ enum TriFlags {
 // clip the k-block range [lo, hi) (units of 4, tile-global) for this warp
 __device__ __forceinline__ void tri_clip(int flags, const WarpPos& w, int& lo,
                                          int& hi) {
-  if (flags & TRI_A_KLE) hi = min(hi, 8 * (w.wm + 1));
-  if (flags & TRI_A_KGE) lo = max(lo, 8 * w.wm);
+  if (w.fullk) {  // 16-row groups
+    const int r4 = 2 * w.wm + w.wk;
+    if (flags & TRI_A_KLE) hi = min(hi, 4 * (r4 + 1));
+    if (flags & TRI_A_KGE) lo = max(lo, 4 * r4);
+  } else {
+    if (flags & TRI_A_KLE) hi = min(hi, 8 * (w.wm + 1));
+    if (flags & TRI_A_KGE) lo = max(lo, 8 * w.wm);
+  }
   if (flags & TRI_B_KLE) hi = min(hi, 8 * (w.wn + 1));
   if (flags & TRI_B_KGE) lo = max(lo, 8 * w.wn);
   if ((flags & TRI_SYM_LOWER) && w.wm == 0 && w.wn == 1) hi = lo;
