@@ -73,9 +73,11 @@ class AdamTrainer:
     self.scal = torch.zeros(4, device=dev, dtype=dt)
     self.allreduce = allreduce
     self.tie_lengthscale = tie_lengthscale
-    self._graph = None
-    self._graph_key = None
+    self._graphs = {}
     self._graph_failed = False
+    self._copy_stream = None
+    self._host_bufs = None
+    self._host_step = 0
     self._loss_pin = None
     self._loss_evt = None
     self._nsteps = 0
@@ -98,7 +100,7 @@ class AdamTrainer:
   def _graphed(self, key, fn):
     """Capture fn() once into a CUDA graph (after an eager warm-up that sizes
     the engine workspace) and replay it afterwards."""
-    if self._graph is None or self._graph_key != key:
+    if key not in self._graphs:
       tensors = (self.raw, self.m, self.v, self.accepted, self.scal)
       state = [t.clone() for t in tensors]
       s = torch.cuda.Stream(device=self.eng.device)
@@ -114,8 +116,10 @@ class AdamTrainer:
         fn()
       for t, c in zip(tensors, state):
         t.copy_(c)
-      self._graph, self._graph_key = g, key
-    self._graph.replay()
+      if len(self._graphs) >= 4:  # bounded cache (a new batch object per step)
+        self._graphs.pop(next(iter(self._graphs)))
+      self._graphs[key] = g
+    self._graphs[key].replay()
 
   def _graph_ok(self, use_graph):
     # Multi-GPU steps stay eager: capturing the NCCL all-reduce into the graph
@@ -133,7 +137,7 @@ class AdamTrainer:
     except RuntimeError as e:  # capture not possible here: stay eager
       logging.warning("CUDA-graph capture failed (%s); using eager launches", e)
       self._graph_failed = True
-      self._graph = None
+      self._graphs = {}
       torch.cuda.synchronize(self.eng.device)
       fn()
 
@@ -148,13 +152,36 @@ class AdamTrainer:
     This is the shape of the reference's loop, where every step receives a
     fresh (sub-sampled) batch from the host iterator (gp.py:133)."""
 
-    def fn():
-      ds.x.copy_(x_host, non_blocking=True)
-      ds.y.copy_(y_host, non_blocking=True)
-      self._enqueue(ds)
-
-    self._run(("host", id(ds), x_host.data_ptr(), y_host.data_ptr()), fn,
-              use_graph)
+    # Double-buffered upload on a copy stream: the H2D copy of THIS step's batch
+    # overlaps the previous step's kernels (it lands in the buffer that step
+    # k-2 used); the compute stream waits for it, then runs the step.
+    dev = self.eng.device
+    if self._host_bufs is None or self._host_bufs[0] is not ds:
+      other = _engine.PackedDataset(ds.keys, torch.empty_like(ds.x),
+                                    torch.empty_like(ds.y), ds.offs)
+      self._host_bufs = (ds, other)
+      self._copy_stream = torch.cuda.Stream(device=dev)
+      self._copied = [torch.cuda.Event() for _ in range(2)]
+      self._read_done = [None, None]
+      self._host_step = 0
+    b = self._host_step & 1
+    buf = self._host_bufs[b]
+    cur = torch.cuda.current_stream(dev)
+    cs = self._copy_stream
+    if self._read_done[b] is not None:
+      cs.wait_event(self._read_done[b])
+    else:
+      cs.wait_stream(cur)
+    with torch.cuda.stream(cs):
+      buf.x.copy_(x_host, non_blocking=True)
+      buf.y.copy_(y_host, non_blocking=True)
+      self._copied[b].record(cs)
+    cur.wait_event(self._copied[b])
+    self._run(("dev", id(buf)), lambda: self._enqueue(buf), use_graph)
+    if self._read_done[b] is None:
+      self._read_done[b] = torch.cuda.Event()
+    self._read_done[b].record(cur)
+    self._host_step += 1
 
   def loss(self) -> float:
     return float(self.scal[0])  # device -> host sync (gp.py:135-138)

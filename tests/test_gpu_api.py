@@ -276,3 +276,51 @@ def test_simulated_bo_loop_shape():  # bayesopt.py:137-193 caller pattern
     idx = int(evals.argmax())
     model.update_sub_dataset((xq[idx], yq[idx]), 0, is_append=True)
   assert model.dataset[0].x.shape == (28, d)
+
+
+def test_adam_trainer_host_batches_double_buffered():
+  """AdamTrainer.step_from_host uploads every step's batch on a copy stream
+  into one of two device buffers (overlapping the previous step's kernels):
+  with a DIFFERENT batch per step the losses must equal the same steps taken on
+  device-resident copies of those batches."""
+  from hyperbo_b200.engine import Engine, PackedDataset
+  eng = Engine.get()
+  d, n, T = 3, 70, 5
+  rng = np.random.default_rng(11)
+  offs = [n * t for t in range(T + 1)]
+  batches = [(torch.from_numpy(rng.random((T * n, d))).pin_memory(),
+              torch.from_numpy(rng.standard_normal(T * n)).pin_memory())
+             for _ in range(5)]
+  raw0 = np.array([0.1, 0.2, -2.0, 0.3, -0.2, 0.1])
+  mask = H.default_mask(d)
+
+  def run(from_host, use_graph):
+    tr = gp.AdamTrainer(eng, 2, 1, raw0, mask, d, 1e-2)
+    ds = PackedDataset(list(range(T)), batches[0][0].to(eng.device),
+                       batches[0][1].to(eng.device), offs)
+    losses = []
+    for xh, yh in batches:
+      if from_host:
+        prev = tr.step_pipelined(ds, xh, yh, use_graph=use_graph)
+        if prev is not None:
+          losses.append(prev)
+      else:
+        dsk = PackedDataset(list(range(T)), xh.to(eng.device), yh.to(eng.device),
+                            offs)
+        tr.step(dsk)
+        losses.append(tr.loss())
+    if from_host:
+      losses.append(tr.flush())
+    return np.array(losses), _np(tr.raw)
+
+  l_dev, r_dev = run(False, False)
+  for use_graph in (False, True):
+    l_host, r_host = run(True, use_graph)
+    assert np.array_equal(l_dev, l_host), use_graph
+    assert np.array_equal(r_dev, r_host), use_graph
+  # and against the oracle for the first batch
+  ds_np = {t: (batches[0][0].numpy()[n * t:n * (t + 1)],
+               batches[0][1].numpy()[n * t:n * (t + 1), None]) for t in range(T)}
+  v_ref = O.neg_log_marginal_likelihood(
+      "constant", "matern52", H.model_from_raw(raw0, d, "constant"), ds_np, WFO)
+  assert abs(l_dev[0] - v_ref) < 1e-10 * abs(v_ref)
