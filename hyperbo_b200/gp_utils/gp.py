@@ -128,8 +128,8 @@ class AdamTrainer:
       return False
     return not self.allreduce or os.environ.get("HB_GRAPH_NCCL", "0") == "1"
 
-  def _run(self, key, fn, use_graph):
-    if not self._graph_ok(use_graph):
+  def _run(self, key, fn, use_graph, force=False):
+    if not (force or self._graph_ok(use_graph)):
       fn()
       return
     try:
@@ -143,6 +143,23 @@ class AdamTrainer:
 
   def step(self, ds, use_graph=False):
     """Enqueue one optimiser step on the current stream."""
+    if (use_graph and self.allreduce and not self._graph_failed and
+        not isinstance(ds, obj.ObjectiveProgram) and
+        os.environ.get("HB_GRAPH_NCCL", "0") != "1"):
+      # several ranks: the kernel sequence of hb_nll_grad_batched replays from a
+      # CUDA graph (short, dependent launches: the gaps between them matter
+      # most when each rank holds few tasks); the all-reduce and the Adam
+      # kernel stay eager (capturing the NCCL call hung on the test box).
+      self._run(("nll", id(ds)),
+                lambda: self.eng.nll_grad(self.kid, self.mid, ds, self.raw,
+                                          self.mask, sums_out=self.sums),
+                True, force=True)
+      import torch.distributed as dist
+      dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)
+      self.eng.adam_step(self.P, self.raw, self.m, self.v, self.accepted,
+                         self.sums, self.scal, self.lr, self.b1, self.b2,
+                         self.eps, self.tie_lengthscale)
+      return
     self._run(("dev", id(ds)), lambda: self._enqueue(ds), use_graph)
 
   def step_from_host(self, ds, x_host: torch.Tensor, y_host: torch.Tensor,
@@ -177,7 +194,7 @@ class AdamTrainer:
       buf.y.copy_(y_host, non_blocking=True)
       self._copied[b].record(cs)
     cur.wait_event(self._copied[b])
-    self._run(("dev", id(buf)), lambda: self._enqueue(buf), use_graph)
+    self.step(buf, use_graph=use_graph)
     if self._read_done[b] is None:
       self._read_done[b] = torch.cuda.Event()
     self._read_done[b].record(cur)
