@@ -375,7 +375,11 @@ def run_ours(args):
       "clocks": clocks,
       "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
               "h2d_bytes_per_step": int((x_host.numel() + y_host.numel()) * esz),
-              "d2h_bytes_per_step": esz},
+              "d2h_bytes_per_step": esz,
+              "path": "gp.AdamTrainer.step_pipelined(ds, x_host, y_host): every "
+                      "step uploads its batch from pinned host memory on a copy "
+                      "stream into one of two device buffers (overlapping the "
+                      "previous step's kernels) and reads its loss back"},
       "gpu_launches": int(launches_per_step * args.steps),
       "gpu_launches_per_step": int(launches_per_step),
       "roofline": roofline,

@@ -179,6 +179,14 @@ __device__ __forceinline__ void tri_clip(int flags, const WarpPos& w, int& lo,
   if ((flags & TRI_SYM_LOWER) && w.wm == 0 && w.wn == 1) hi = lo;
 }
 
+// symmetric output (TRI_SYM_LOWER), full-K mapping: how many of the warp's four
+// 8-column blocks hold entries on or below the diagonal of its 16 rows
+__device__ __forceinline__ int sym_nfn(int flags, const WarpPos& w) {
+  if (!(flags & TRI_SYM_LOWER) || !w.fullk) return 4;
+  const int r4 = 2 * w.wm + w.wk;
+  return max(0, min(4, 2 * (r4 + 1) - 4 * w.wn));
+}
+
 // offset of the MN-major fragment (k-block kl, idx-block blk8) inside a buffer
 // whose rows are the contraction index and whose row-blocks hold 16 col-blocks
 __device__ __forceinline__ int mn_off(int blk8, int kl, int g, int t) {

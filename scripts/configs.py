@@ -51,6 +51,13 @@ def c4():
   g = gp.GP(dataset, mean.constant, kernel.matern52,
             defs.GPParams(model=dict(model0), config=dict(cfg)),
             utils.DEFAULT_WARP_FUNC)
+  # untimed warm-up of the same shapes (module load, workspace, local-memory
+  # set-up); the timed run below still captures its own CUDA graph
+  warm_cfg = dict(cfg)
+  warm_cfg["max_training_step"] = 3
+  gp.GP(dataset, mean.constant, kernel.matern52,
+        defs.GPParams(model=dict(model0), config=warm_cfg),
+        utils.DEFAULT_WARP_FUNC).train()
   losses = []
   torch.cuda.synchronize()
   t0 = time.perf_counter()
