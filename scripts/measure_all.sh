@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-end measurement set (one B200): bench lines, ncu launch lists, ncu --set full
-TAG=${TAG:-r1n}
+TAG=${TAG:-r1o}
 O=gpurun_out
 M="gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum"
 timeout 300 python bench.py --steps 50 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
