@@ -54,8 +54,43 @@ def solve_gp_linear_system(mean_func, cov_func, params, x, y, warp_func=None,
   return chol, kinvy, dy
 
 
+# ---- explicit-matrix helpers (linalg.py:29-33,112-197) ----------------------
+# Off the hot path: the engine never materialises K (solve_gp_linear_system
+# builds and factorises it tile by tile).  These operate on matrices the caller
+# already holds (e.g. the data-side moments of the KL objective) and are plain
+# torch calls (cuSOLVER / cuBLAS on CUDA tensors).
+def cholesky_cache(spd_matrix, cached_cholesky):
+  """Cholesky factor of `spd_matrix` unless one is given (linalg.py:129-136)."""
+  if cached_cholesky is not None:
+    return cached_cholesky
+  return torch.linalg.cholesky(spd_matrix)
+
+
+def inverse_spdmatrix_vector_product(spd_matrix, x, cached_cholesky=None):
+  """spd_matrix^-1 x through the Cholesky factor (linalg.py:139-145)."""
+  chol = cholesky_cache(spd_matrix, cached_cholesky)
+  x = torch.as_tensor(x, dtype=chol.dtype, device=chol.device)
+  if x.dim() == 1:
+    return torch.cholesky_solve(x[:, None], chol)[:, 0]
+  return torch.cholesky_solve(x, chol)
+
+
 def solve_linear_system(coeff, b):
-  raise NotImplementedError(
-      "solve_linear_system on an explicit matrix is not part of the engine's "
-      "hot path; use solve_gp_linear_system (the kernel matrix is built and "
-      "factorised on the GPU without being materialised)")
+  """Solve A x = b for SPD A = coeff -> (chol, x)  (linalg.py:29-33)."""
+  chol = torch.linalg.cholesky(coeff)
+  return chol, inverse_spdmatrix_vector_product(coeff, b, cached_cholesky=chol)
+
+
+def svd_matrix_sqrt(cov):
+  """A with A A' = cov and full column rank (linalg.py:112-126)."""
+  u, s, _ = torch.linalg.svd(cov)
+  factor = u * torch.sqrt(s)[None, :]
+  tol = s.max() * torch.finfo(s.dtype).eps / 2.0 * (2 * cov.shape[0] + 1.0)**0.5
+  rank = int((s > tol).sum())
+  return factor[:, :rank]
+
+
+def safe_l2norm(x):
+  """l2 norm (linalg.py:194-197; the custom gradient at 0 only matters to
+  autodiff, which the engine replaces by closed forms)."""
+  return torch.sqrt(torch.sum(torch.as_tensor(x)**2))

@@ -84,6 +84,24 @@ matern32_kumar = _unsupported("matern32_kumar", "Kumaraswamy warp")
 matern52_kumar = _unsupported("matern52_kumar", "Kumaraswamy warp")
 
 
+def covariance_matrix(kernel):
+  """Decorator of the reference that turns a pairwise kernel into a matrix map
+  (kernel.py:29-60).  The engine evaluates its kernels tile by tile on the GPU
+  and differentiates them in closed form, so it cannot adopt an arbitrary Python
+  pairwise function: use squared_exponential / matern32 / matern52."""
+  raise NotImplementedError(
+      f"custom pairwise kernel {getattr(kernel, '__name__', kernel)!r}: the "
+      "engine's kernels are built in (squared_exponential, matern32, matern52)")
+
+
+def with_mlp_bases(kernel):  # kernel.py:148-176
+  raise NotImplementedError("learned MLP input warps are outside the hot path")
+
+
+def with_kumar_bases(kernel):  # kernel.py:179-209
+  raise NotImplementedError("Kumaraswamy input warps are outside the hot path")
+
+
 def kernel_id_of(cov_func) -> int:
   kid = getattr(cov_func, "hb_kernel_id", None)
   if kid is None:

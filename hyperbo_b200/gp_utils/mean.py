@@ -54,6 +54,14 @@ linear = _unsupported("linear")
 linear_mlp = _unsupported("linear_mlp")
 
 
+def mean_vector(mean_func):
+  """Decorator of the reference that maps a per-point mean over the rows of x
+  (mean.py:30-51).  The engine's means are built in (zero, constant)."""
+  raise NotImplementedError(
+      f"custom mean function {getattr(mean_func, '__name__', mean_func)!r}: "
+      "the engine's means are built in (zero, constant)")
+
+
 def mean_id_of(mean_func) -> int:
   mid = getattr(mean_func, "hb_mean_id", None)
   if mid is None:

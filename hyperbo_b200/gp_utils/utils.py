@@ -8,7 +8,12 @@ from __future__ import annotations
 
 import torch
 
+from hyperbo_b200.basics import data_utils as _data_utils
+from hyperbo_b200.basics import definitions as _defs
+
 EPS = 1e-10  # utils.py:28
+SubDataset = _defs.SubDataset  # utils.py:23
+sub_sample_dataset_iterator = _data_utils.sub_sample_dataset_iterator  # utils.py:32
 
 
 def identity_warp(x):
@@ -31,6 +36,11 @@ def DEFAULT_SOFTPLUS(x):  # utils.py:73
 
 
 DEFAULT_SOFTPLUS.hb_warp = "softplus_eps"
+
+
+def squareplus_warp(x):  # utils.py:30 -- a plain callable: the engine does not
+  x = torch.as_tensor(x, dtype=torch.float64)  # differentiate it (warp_kind raises)
+  return 0.5 * (x + torch.sqrt(x**2 + 4))
 
 # utils.py:75-81
 DEFAULT_WARP_FUNC = {
@@ -75,11 +85,8 @@ def partial_kl_mvn(mu0, cov0, mu1, cov1):
 
 def svd_matrix_sqrt(cov):
   """basics/linalg.py:112-126."""
-  u, s, _ = torch.linalg.svd(cov)
-  factor = u * torch.sqrt(s)[None, :]
-  tol = s.max() * torch.finfo(s.dtype).eps / 2.0 * (2 * cov.shape[0] + 1.0)**0.5
-  rank = int((s > tol).sum())
-  return factor[:, :rank]
+  from hyperbo_b200.basics import linalg as _linalg
+  return _linalg.svd_matrix_sqrt(cov)
 
 
 def kl_multivariate_normal(mu0, cov0, mu1, cov1, weight=1.0, eps=0.0,
