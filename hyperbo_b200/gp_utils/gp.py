@@ -744,6 +744,28 @@ class HGP(GP):
   def get_model_params_samples(self):
     return self.params.samples if self.params.samples else [self.params.model]
 
+  def stats(self, verbose=True):
+    """Objective stats averaged over the hyper-parameter samples (gp.py:634-664)."""
+    import collections
+    samples = self.get_model_params_samples()
+    all_stats, all_key2nll, key2nll = [], collections.defaultdict(float), {}
+    for model_params in samples:
+      self.update_model_params(model_params)
+      nll, ekl, ekl_partial, euc, key2nll = super().stats(verbose=verbose)
+      all_stats.append((nll, ekl, ekl_partial, euc))
+      for k in key2nll:
+        all_key2nll[k] += key2nll[k]
+    for k in key2nll:
+      all_key2nll[k] /= len(samples)
+    nll, ekl, ekl_partial, euc = (float(v) for v in np.mean(
+        np.asarray(all_stats, dtype=np.float64), axis=0))
+    msg = (f"HGP nll = {nll}, ekl = {ekl}, ekl_partial = {ekl_partial}, euc ="
+           f" {euc}")
+    if verbose:
+      print(msg)
+    logging.info(msg=msg)
+    return nll, ekl, ekl_partial, euc, all_key2nll
+
   def predict(self, queried_inputs, sub_dataset_key=0, full_cov=False,
               with_noise=True):
     results = []
