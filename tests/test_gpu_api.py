@@ -324,3 +324,42 @@ def test_adam_trainer_host_batches_double_buffered():
   v_ref = O.neg_log_marginal_likelihood(
       "constant", "matern52", H.model_from_raw(raw0, d, "constant"), ds_np, WFO)
   assert abs(l_dev[0] - v_ref) < 1e-10 * abs(v_ref)
+
+
+@pytest.mark.parametrize("name", ["expected_improvement", "ucb",
+                                  "probability_of_improvement"])
+def test_acfun_over_hyperparameter_sets(name):
+  """acfun_test.py:74-118 evaluates an acquisition for 100 (constant,
+  lengthscale) sets with jax.vmap.  The engine cannot be traced by vmap; the
+  same sweep is a host loop over update_model_params (each set = one factorise
+  + one fused predict/acquisition launch sequence)."""
+  rng = np.random.default_rng(0)
+  nx, nq, dim, S = 20, 10, 5, 12
+  vx = rng.normal(size=(nx, dim))
+  truth = defs.GPParams(model={"constant": 5., "lengthscale": 0.1,
+                               "signal_variance": 1.0, "noise_variance": 0.01})
+  vy = gp.sample_from_gp(3, mean.constant, kernel.squared_exponential, truth, vx)
+  xq = rng.normal(size=(nq, dim))
+  sets = [np.hstack([rng.uniform(-10., 10.), rng.gamma(1., 1., (dim,)) + 0.05])
+          for _ in range(S)]
+  model = gp.GP(dataset=[(vx, vy)], mean_func=mean.constant,
+                cov_func=kernel.squared_exponential,
+                params=defs.GPParams(model=dict(truth.model)))
+  f = const.ACFUN[name]
+  evals = []
+  for cl in sets:
+    model.update_model_params({"constant": float(cl[0]), "lengthscale": cl[1:],
+                               "signal_variance": 1.0, "noise_variance": 0.01})
+    evals.append(f(model=model, sub_dataset_key=0, x_queries=xq))
+  evals = torch.stack(evals)
+  assert evals.shape == (S, nq, 1)
+  ds_np = {0: (vx, _np(vy))}
+  oname = {"expected_improvement": "ei", "ucb": "ucb",
+           "probability_of_improvement": "pi"}[name]
+  for s in (0, S - 1):
+    m = {"constant": float(sets[s][0]), "lengthscale": sets[s][1:],
+         "signal_variance": 1.0, "noise_variance": 0.01}
+    want = O.acquisition(oname, "constant", "squared_exponential", m, ds_np, 0,
+                         xq, None)
+    assert np.max(np.abs(_np(evals[s]) - want)) < 1e-6 * (
+        np.max(np.abs(want)) + 1e-3), (name, s)

@@ -183,3 +183,74 @@ def test_weighted_call_and_jitter():
   a = eng.nll_grad(1, 1, ds, raw, 0).cpu().numpy()
   b = eng.nll_grad(1, 1, ds, raw, 0, weights=np.ones(3), jitter=O.JITTER).cpu().numpy()
   assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("cov", sorted(COVS))
+def test_sample_mean_cov_regularizer(cov):
+  """Port of objectives_test.py:67-196 (kl distance, lbfgs; the engine kernels):
+  10 GP samples on shared inputs form ONE aligned sub-dataset; training on the
+  divergence decreases it; the SVD NLL agrees with the Cholesky NLL (evaluated
+  with exclude_aligned=False on the (n, 10) y, objectives.py:153-155)."""
+  n = 20
+  vx = np.random.default_rng(0).normal(size=(n, 2))
+  truth = defs.GPParams(model={"constant": 5., "lengthscale": 1.,
+                               "signal_variance": 1.0, "noise_variance": 0.01})
+  cf = COVS[cov]
+  vy = gp.sample_from_gp(1, mean.constant, cf, truth, vx, num_samples=10)
+  assert vy.shape == (n, 10)
+  dataset = [(vx, vy, "all_data")]
+  distance = utils.kl_multivariate_normal
+  init = defs.GPParams(
+      model={"constant": 5.1, "lengthscale": 0., "signal_variance": 0.,
+             "noise_variance": -4.},
+      config={"method": "lbfgs", "max_training_step": 2, "logging_interval": 1,
+              "objective": functools.partial(
+                  objectives.multivariate_normal_divergence, distance=distance),
+              "batch_size": 100, "learning_rate": 0.001})
+  model = gp.GP(dataset=dataset, mean_func=mean.constant, cov_func=cf,
+                params=init, warp_func=WF)
+
+  def reg(p, wf=None):
+    return float(objectives.multivariate_normal_divergence(
+        mean_func=model.mean_func, cov_func=model.cov_func, params=p,
+        dataset=model.dataset, warp_func=wf, distance=distance))
+
+  def nll_func(p, wf=None, use_cholesky=True):
+    return float(objectives.neg_log_marginal_likelihood(
+        mean_func=model.mean_func, cov_func=model.cov_func, params=p,
+        dataset=model.dataset, warp_func=wf, use_cholesky=use_cholesky,
+        exclude_aligned=False))
+
+  assert np.isfinite(reg(truth)) and np.isfinite(nll_func(truth))
+  init_reg = reg(init, WF)
+  init_nll = nll_func(init, WF)
+  assert abs(nll_func(init, WF, use_cholesky=False) / init_nll - 1.) < 5e-3
+  # the multi-column value equals the oracle's literal restatement
+  ds_np = {0: (vx, vy.cpu().numpy(), 0)}
+  want = O.neg_log_marginal_likelihood("constant", cov, dict(init.model), ds_np,
+                                       WFO, exclude_aligned=False)
+  assert abs(init_nll - want) < 1e-9 * abs(want)
+  inferred = model.train()
+  inferred_reg = reg(inferred, WF)
+  inferred_nll = nll_func(inferred, WF)
+  assert abs(nll_func(inferred, WF, use_cholesky=False) / inferred_nll - 1.) < 5e-3
+  assert init_reg > inferred_reg
+
+
+def test_hgp_stats_average_over_samples():  # gp.py:634-664
+  g, model, params, dataset, mf, cf = _case("kl_m52_const_d3")
+  other = dict(model)
+  other["signal_variance"] = model["signal_variance"] + 0.3
+  single = [gp.GP(dataset=dataset, mean_func=mf, cov_func=cf,
+                  params=defs.GPParams(model=dict(m)), warp_func=WF
+                  ).stats(verbose=False) for m in (model, other)]
+  hgp = gp.HGP(dataset=dataset, mean_func=mf, cov_func=cf,
+               params=defs.GPParams(model=dict(model),
+                                    samples=[dict(model), dict(other)]),
+               warp_func=WF)
+  nll, ekl, ekl_partial, euc, key2nll = hgp.stats(verbose=False)
+  for got, i in ((nll, 0), (ekl, 1), (ekl_partial, 2), (euc, 3)):
+    want = 0.5 * (single[0][i] + single[1][i])
+    assert abs(got - want) < 1e-12 * abs(want)
+  for k in key2nll:
+    assert abs(key2nll[k] - 0.5 * (single[0][4][k] + single[1][4][k])) < 1e-9
