@@ -124,7 +124,7 @@ class AdamTrainer:
   def _graph_ok(self, use_graph):
     # Multi-GPU steps stay eager: capturing the NCCL all-reduce into the graph
     # hung on the 2-GPU test box (round 1), so it is opt-in (HB_GRAPH_NCCL=1).
-    if not use_graph or self._graph_failed:
+    if not use_graph or self._graph_failed or self.eng.device.type != "cuda":
       return False
     return not self.allreduce or os.environ.get("HB_GRAPH_NCCL", "0") == "1"
 
@@ -144,6 +144,7 @@ class AdamTrainer:
   def step(self, ds, use_graph=False):
     """Enqueue one optimiser step on the current stream."""
     if (use_graph and self.allreduce and not self._graph_failed and
+        self.eng.device.type == "cuda" and
         not isinstance(ds, obj.ObjectiveProgram) and
         os.environ.get("HB_GRAPH_NCCL", "0") != "1"):
       # several ranks: the kernel sequence of hb_nll_grad_batched replays from a

@@ -338,8 +338,7 @@ def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
       raise NotImplementedError(
           "the Euclidean regulariser (objectives.py:104-106) is value-only "
           "here (GP.stats); it has no engine program / gradient")
-  if rank != 0:
-    const = 0.0  # added once: the partial vectors are summed over ranks
+  # (const is added by every rank AFTER the all-reduce of the partial vectors)
   return ObjectiveProgram(eng, kid, d or 1, launches, const, world, trace_terms)
 
 

@@ -1,0 +1,117 @@
+"""A CPU stand-in for hyperbo_b200.engine.Engine -- TEST INFRASTRUCTURE ONLY.
+
+It answers `nll_grad` (the hb_nll_grad_batched / hb_nll_grad_weighted contract:
+weighted sums of per-task NLL values and raw-parameter gradients, runtime
+jitter) with the oracle's arithmetic on CPU tensors, so that the HOST logic
+built on top of the engine -- objective programs, task sharding, the
+all-reduce contract -- runs under `-m "not gpu"` and under gloo.  The product
+never imports this module; on a GPU box the same host logic drives the CUDA
+kernels (tests/test_gpu_objectives.py)."""
+import math
+
+import numpy as np
+import scipy.linalg as spla
+import torch
+
+from hyperbo_b200 import engine as _engine
+from oracle import hyperbo_oracle as O
+
+_KERNELS = {v: k for k, v in _engine.KERNEL_IDS.items()}
+
+
+def task_nll_and_grad(kid, mid, x, y, raw, mask, jitter):
+  """nll and d nll / d raw (length 3 + d) of one task, closed form."""
+  n, d = x.shape
+  raw = np.asarray(raw, dtype=np.float64)
+  warped = np.array([(mask >> p) & 1 for p in range(3 + d)], dtype=bool)
+  theta = np.where(warped, O.softplus(raw) + O.EPS_WARP, raw)
+  chain = np.where(warped, O.sigmoid(raw), 1.0)
+  c = theta[0] if mid == 1 else 0.0
+  sv, nv, ls = theta[1], theta[2], theta[3:]
+  name = _KERNELS[kid]
+  r2, diff = O._scaled_sqdist(x, x, ls)  # pylint: disable=protected-access
+  k = O._kernel_from_r2(name, r2, sv)  # pylint: disable=protected-access
+  chol = np.linalg.cholesky(k + np.eye(n) * (nv + jitter))
+  r = (y - c)[:, None]
+  alpha = spla.cho_solve((chol, True), r)
+  nll = float(0.5 * (r.T @ alpha).item() + np.sum(np.log(np.diag(chol))) +
+              0.5 * n * math.log(2 * math.pi))
+  g = 0.5 * (spla.cho_solve((chol, True), np.eye(n)) - alpha @ alpha.T)
+  w = O._pair_weight(name, r2, k, sv)  # pylint: disable=protected-access
+  grad = np.zeros(3 + d)
+  grad[0] = -float(np.sum(alpha)) if mid == 1 else 0.0
+  grad[1] = float(np.sum(g * k) / sv)
+  grad[2] = float(np.trace(g))
+  grad[3:] = np.einsum("ij,ijk->k", g * w, diff * diff) / ls
+  return nll, grad * chain
+
+
+class FakeEngine(_engine.Engine):
+  """Engine whose arithmetic is the oracle's (CPU, fp64)."""
+
+  def __init__(self):  # pylint: disable=super-init-not-called
+    self.device = torch.device("cpu")
+    self.dtype = torch.float64
+    self.max_dim = 32
+    self.calls = 0
+
+  def nll_grad(self, kernel_id, mean_id, ds, raw, mask, sums_out=None,
+               want_task_nll=False, weights=None, jitter=None):
+    raw = np.asarray(torch.as_tensor(raw).detach().cpu(), dtype=np.float64)
+    jitter = O.JITTER if jitter is None else float(jitter)
+    T, P = ds.num_tasks, 3 + ds.d
+    w = np.ones(T) if weights is None else np.asarray(
+        torch.as_tensor(weights).cpu(), dtype=np.float64)
+    out = np.zeros(P + 2)
+    per_task = np.zeros(T)
+    x, y = ds.x.numpy(), ds.y.numpy()
+    for t in range(T):
+      lo, hi = ds.offs[t], ds.offs[t + 1]
+      v, g = task_nll_and_grad(kernel_id, mean_id, x[lo:hi], y[lo:hi], raw, mask,
+                               jitter)
+      out[0] += w[t] * v
+      out[1:-1] += w[t] * g
+      out[-1] += 1.0
+      per_task[t] = v
+    self.calls += 1
+    res = torch.from_numpy(out)
+    if sums_out is not None:
+      sums_out.copy_(res)
+      res = sums_out
+    if want_task_nll:
+      return res, torch.from_numpy(per_task)
+    return res
+
+
+  def adam_step(self, P, raw, m, v, accepted, sums, scal, lr, b1=0.9, b2=0.999,
+                eps=1e-8, tie_lengthscale=False):
+    """hb_adam_step (k_adam): optax.adam + the accept / stop rule of
+    gp.py:135-146, in place on CPU tensors."""
+    cnt = float(sums[1 + P])
+    loss = float(sums[0]) / cnt if cnt > 0 else 0.0
+    stopped = bool(scal[2] != 0)
+    scal[0] = loss
+    if stopped:
+      return
+    if not math.isfinite(loss):
+      scal[2] = 1.0
+      return
+    t = float(scal[1]) + 1.0
+    scal[1] = t
+    scal[3] += 1.0
+    g = sums[1:1 + P].clone() / cnt if cnt > 0 else torch.zeros(P, dtype=raw.dtype)
+    if tie_lengthscale:
+      g[3:] = g[3:].sum()
+    accepted.copy_(raw)
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    mhat = m / (1 - b1**t)
+    vhat = v / (1 - b2**t)
+    raw.sub_(lr * mhat / (torch.sqrt(vhat) + eps))
+
+
+def install(monkeypatch):
+  """Route Engine.get() to one FakeEngine for the duration of a test."""
+  eng = FakeEngine()
+  monkeypatch.setattr(_engine.Engine, "get", staticmethod(lambda *a, **k: eng))
+  return eng
