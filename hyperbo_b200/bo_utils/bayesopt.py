@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import logging
 import time
-from typing import Any, Callable, Optional, Union
 
 import numpy as np
 import scipy.optimize

@@ -3,7 +3,6 @@
 (the datasets are not part of the reference tree)."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from hyperbo_b200.basics import definitions as defs

@@ -15,7 +15,7 @@ from __future__ import annotations
 import logging
 import math
 import os
-from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+from typing import Any, Dict, List, Union
 
 import numpy as np
 import torch
