@@ -144,6 +144,14 @@ def cpu_port_steps_per_sec(sample_tasks, steps, warmup, dtype_name="f64"):
   and scales to the full 256-task step."""
   import torch
   from oracle import hyperbo_oracle_torch as OT
+  # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1
+  # to its workers: a launcher default, not a property of the baseline)
+  try:
+    ncores = len(os.sched_getaffinity(0))
+  except AttributeError:
+    ncores = os.cpu_count() or 1
+  if torch.get_num_threads() < ncores:
+    torch.set_num_threads(ncores)
   x, y = synthetic_batch(sample_tasks, N_PTS, DIM)
   model = {"constant": 5.1, "lengthscale": [0.0] * DIM, "signal_variance": 0.0,
            "noise_variance": -4.0}
