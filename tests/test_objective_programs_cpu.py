@@ -245,3 +245,32 @@ def test_lbfgs_on_ekl_matches_the_driver_on_the_oracle(monkeypatch):
   _, v, _ = _lbfgs.lbfgs(val_and_grad, H.raw_vec(model, d), steps=3, alpha=1.0)
   assert H.rel(H.raw_vec({k: np.asarray(x) for k, x in out.model.items()}, d),
                v) < 1e-8
+
+
+def test_subsampled_training_rebuilds_the_program_every_step(monkeypatch):
+  """batch_size <= n: data_utils.sub_sample_dataset_iterator draws new rows of
+  every sub-dataset per step (data_utils.py:72-100), so the objective program
+  is recompiled per step; the losses equal the oracle's on the same batches.
+  Also: the objective given by NAME (GP.initialize_params resolves strings)."""
+  from hyperbo_b200.basics import data_utils
+  from hyperbo_b200.gp_utils import gp
+  fake_engine.install(monkeypatch)
+  g, model, params, dataset = _case("kl_m52_const_d3")
+  params.config = {"method": "adam", "learning_rate": 1e-2,
+                   "max_training_step": 3, "batch_size": 25}
+  losses = []
+  gp.infer_parameters(mean.constant, kernel.matern52, params, dataset, WF,
+                      objective="ekl", key=5,
+                      callback=lambda i, p, l: losses.append(l))
+  it = data_utils.sub_sample_dataset_iterator(
+      5, {k: defs.SubDataset(*v) for k, v in dataset.items()}, 25)
+  opt, m, want = O.Adam(1e-2), dict(model), []
+  for _ in range(3):
+    batch = next(it)
+    b_np = {k: (np.asarray(s.x), np.asarray(s.y), s.aligned)
+            for k, s in batch.items()}
+    assert all(s[0].shape[0] <= 25 for s in b_np.values())
+    v, gr = O.kl_value_and_grad("constant", "matern52", m, b_np, WFO)
+    want.append(v)
+    m = opt.update(m, gr)
+  assert H.rel(losses, want) < 1e-10
