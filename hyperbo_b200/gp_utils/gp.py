@@ -400,7 +400,7 @@ def infer_parameters(mean_func,
       return False
     return True
 
-  if callback is None and not needs_subsample:
+  if callback is None and not needs_subsample and eng.device.type == "cuda":
     # one step ahead of the loss read-back (see AdamTrainer.step_pipelined)
     for i in range(max_training_step):
       prev = trainer.step_pipelined(ds, use_graph=True)

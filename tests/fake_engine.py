@@ -31,7 +31,10 @@ def task_nll_and_grad(kid, mid, x, y, raw, mask, jitter):
   name = _KERNELS[kid]
   r2, diff = O._scaled_sqdist(x, x, ls)  # pylint: disable=protected-access
   k = O._kernel_from_r2(name, r2, sv)  # pylint: disable=protected-access
-  chol = np.linalg.cholesky(k + np.eye(n) * (nv + jitter))
+  try:
+    chol = np.linalg.cholesky(k + np.eye(n) * (nv + jitter))
+  except np.linalg.LinAlgError:  # engine contract: NaN propagates, no raise
+    return float("nan"), np.full(3 + d, np.nan)
   r = (y - c)[:, None]
   alpha = spla.cho_solve((chol, True), r)
   nll = float(0.5 * (r.T @ alpha).item() + np.sum(np.log(np.diag(chol))) +
@@ -82,6 +85,102 @@ class FakeEngine(_engine.Engine):
       return res, torch.from_numpy(per_task)
     return res
 
+
+  # ---- the rest of the Engine surface (same contracts as engine.py) ---------
+  @staticmethod
+  def _np(a):
+    return np.asarray(torch.as_tensor(a).detach().cpu(), dtype=np.float64)
+
+  @staticmethod
+  def _theta(raw, mask, d):
+    raw = FakeEngine._np(raw)
+    warped = np.array([(mask >> p) & 1 for p in range(3 + d)], dtype=bool)
+    return np.where(warped, O.softplus(raw) + O.EPS_WARP, raw)
+
+  def _gram(self, kid, x1, x2, theta):
+    r2, _ = O._scaled_sqdist(x1, x2, theta[3:])  # pylint: disable=protected-access
+    return O._kernel_from_r2(_KERNELS[kid], r2, theta[1])  # pylint: disable=protected-access
+
+  def kernel_matrix(self, kernel_id, x1, x2, raw, mask, diag=False,
+                    add_noise=False, jitter=O.JITTER):
+    x1 = self._np(x1)
+    theta = self._theta(raw, mask, x1.shape[1])
+    if x2 is None:
+      if diag:
+        return torch.full((x1.shape[0],), float(theta[1]), dtype=torch.float64)
+      k = self._gram(kernel_id, x1, x1, theta)
+      if add_noise:
+        k = k + np.eye(x1.shape[0]) * (theta[2] + jitter)
+      return torch.from_numpy(k)
+    return torch.from_numpy(self._gram(kernel_id, x1, self._np(x2), theta))
+
+  def _solve(self, kid, mid, x, y, raw, mask):
+    theta = self._theta(raw, mask, x.shape[1])
+    n = x.shape[0]
+    cov = self._gram(kid, x, x, theta) + np.eye(n) * (theta[2] + O.JITTER)
+    r = (y.reshape(-1) - (theta[0] if mid == 1 else 0.0))[:, None]
+    try:
+      chol = np.linalg.cholesky(cov)
+    except np.linalg.LinAlgError:
+      return np.full((n, n), np.nan), np.full((n, 1), np.nan), np.nan, 1
+    alpha = spla.cho_solve((chol, True), r)
+    nll = float(0.5 * (r.T @ alpha).item() + np.sum(np.log(np.diag(chol))) +
+                0.5 * n * math.log(2 * math.pi))
+    return chol, alpha, nll, 0
+
+  def factorize(self, kernel_id, mean_id, ds, raw, mask, want_chol=True,
+                want_alpha=True):
+    x, y = ds.x.numpy(), ds.y.numpy()
+    chols, alphas, nlls, infos = [], [], [], []
+    for t in range(ds.num_tasks):
+      lo, hi = ds.offs[t], ds.offs[t + 1]
+      c, a, v, info = self._solve(kernel_id, mean_id, x[lo:hi], y[lo:hi], raw, mask)
+      chols.append(torch.from_numpy(c))
+      alphas.append(a.reshape(-1))
+      nlls.append(v)
+      infos.append(info)
+    alpha = torch.from_numpy(np.concatenate(alphas)) if alphas else torch.zeros(0)
+    return (chols if want_chol else None, alpha if want_alpha else None,
+            torch.tensor(nlls, dtype=torch.float64),
+            torch.tensor(infos, dtype=torch.int32))
+
+  def build_predictor(self, kernel_id, mean_id, x, y, raw, mask):
+    x, y = self._np(x), self._np(y)
+    chol, alpha, nll, info = self._solve(kernel_id, mean_id, x, y, raw, mask)
+    cache = (chol, alpha)  # opaque to the callers, like the packed device cache
+    return (cache, torch.from_numpy(chol), torch.from_numpy(alpha),
+            torch.tensor([nll]), torch.tensor([info], dtype=torch.int32))
+
+  def _acq(self, acq_id, param, mu, var):
+    std = np.sqrt(var)
+    if acq_id == 1:
+      return O.expected_improvement_sub(mu, std, param)
+    if acq_id == 2:
+      return O.probability_of_improvement_sub(mu, std, param)
+    return O.ucb_sub(mu, std, param)
+
+  def predict(self, kernel_id, mean_id, x, cache, raw, mask, xq, noise_flag=0.0,
+              var_scale=1.0, acq_id=0, acq_param=0.0, want_mu=True,
+              want_var=True):
+    xq = self._np(xq)
+    theta = self._theta(raw, mask, xq.shape[1])
+    mu = np.full((xq.shape[0], 1), theta[0] if mean_id == 1 else 0.0)
+    v2 = np.zeros((xq.shape[0], 1))
+    if x is not None and torch.as_tensor(x).shape[0] > 0:
+      chol, alpha = cache
+      ks = self._gram(kernel_id, self._np(x), xq, theta)
+      mu = mu + ks.T @ alpha
+      v = spla.solve_triangular(chol, ks, lower=True)
+      v2 = np.sum(v * v, axis=0)[:, None]
+    var = (theta[1] - v2 + noise_flag * theta[2]) * var_scale
+    acq = torch.from_numpy(self._acq(acq_id, acq_param, mu, var)) if acq_id \
+        else None
+    return (torch.from_numpy(mu) if want_mu else None,
+            torch.from_numpy(var) if want_var else None, acq)
+
+  def acquisition(self, acq_id, param, mu, var):
+    mu, var = self._np(mu).reshape(-1, 1), self._np(var).reshape(-1, 1)
+    return torch.from_numpy(self._acq(acq_id, float(param), mu, var))
 
   def adam_step(self, P, raw, m, v, accepted, sums, scal, lr, b1=0.9, b2=0.999,
                 eps=1e-8, tie_lengthscale=False):
