@@ -125,3 +125,34 @@ ucb = ucb3
 
 random_search.__name__ = "random_search"
 rand = random_search
+
+
+def shard_candidates(ac_func):
+  """Candidate-axis sharding of an acquisition sweep over the ranks of
+  torch.distributed: the factorisation (L, alpha) is replicated
+  -- every rank holds the same model -- each rank evaluates a contiguous slice
+  of `x_queries`, and one all-gather gives every rank the full (nq, 1) vector,
+  so a following arg-max picks the same candidate everywhere.  Collective: all
+  ranks must call it with the same arguments.  Without an initialised process
+  group (or with one rank) it is `ac_func` itself."""
+
+  def acquisition_function(*, model, sub_dataset_key, x_queries, **kwargs):
+    import torch.distributed as dist
+    rank, world = gp._dist_world()  # pylint: disable=protected-access
+    nq = torch.as_tensor(x_queries).shape[0]
+    if world == 1 or nq < world:
+      return ac_func(model=model, sub_dataset_key=sub_dataset_key,
+                     x_queries=x_queries, **kwargs)
+    chunk = -(-nq // world)
+    lo, hi = min(rank * chunk, nq), min((rank + 1) * chunk, nq)
+    local = ac_func(model=model, sub_dataset_key=sub_dataset_key,
+                    x_queries=x_queries[lo:hi], **kwargs).reshape(-1)
+    padded = torch.zeros(chunk, dtype=local.dtype, device=local.device)
+    padded[:hi - lo] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat(parts)[:nq].reshape(-1, 1)
+
+  acquisition_function.__name__ = getattr(ac_func, "__name__",
+                                          "acquisition_function")
+  return acquisition_function

@@ -274,3 +274,50 @@ def test_subsampled_training_rebuilds_the_program_every_step(monkeypatch):
     want.append(v)
     m = opt.update(m, gr)
   assert H.rel(losses, want) < 1e-10
+
+
+# ---- candidate-axis sharding of an acquisition sweep ----------
+def _acq_case():
+  from hyperbo_b200.gp_utils import gp
+  d = 3
+  ds_np = O.make_dataset(3, 40, d, "matern32")
+  model = gp.GP({k: defs.SubDataset(*v) for k, v in ds_np.items()},
+                mean.constant, kernel.matern32,
+                defs.GPParams(model=dict(O.init_raw_params(d))), WF)
+  xq, _ = O.make_task(77, 101, d, "matern32")  # 101: not a multiple of 2
+  return ds_np, model, xq
+
+
+def _acq_worker(rank, world, port, out):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from hyperbo_b200 import engine as _engine
+  from hyperbo_b200.bo_utils import acfun
+  eng = fake_engine.FakeEngine()
+  _engine.Engine.get = staticmethod(lambda *a, **k: eng)
+  _, model, xq = _acq_case()
+  ei = acfun.shard_candidates(acfun.ei)(model=model, sub_dataset_key=1,
+                                        x_queries=xq)
+  out[rank] = ei.numpy().copy()
+  dist.destroy_process_group()
+
+
+def test_two_rank_candidate_sharding(monkeypatch):
+  from hyperbo_b200.bo_utils import acfun
+  world = 2
+  mgr = mp.Manager()
+  out = mgr.dict()
+  mp.spawn(_acq_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+  assert np.array_equal(out[0], out[1]) and out[0].shape == (101, 1)
+  fake_engine.install(monkeypatch)
+  ds_np, model, xq = _acq_case()
+  full = acfun.ei(model=model, sub_dataset_key=1, x_queries=xq).numpy()
+  assert H.rel(out[0], full) < 1e-12  # (BLAS blocking differs with the slice)
+  want = O.acquisition("ei", "constant", "matern32", O.init_raw_params(3), ds_np,
+                       1, xq, WFO)
+  assert H.rel(full, want) < 1e-9
+  # no process group: the wrapper is the acquisition itself
+  same = acfun.shard_candidates(acfun.ei)(model=model, sub_dataset_key=1,
+                                          x_queries=xq).numpy()
+  assert np.array_equal(same, full)
