@@ -274,3 +274,56 @@ def test_kl_gradient_finite_differences():
           O.multivariate_normal_divergence("constant", "matern52", mm, ds, WF)
           ) / (2 * h)
     assert abs(fd - g["lengthscale"][k]) < 1e-5 * max(1.0, abs(fd)), k
+
+
+# ---- further pure-maths pins (SURVEY.md 8c "extra known-answer checks") -------
+@pytest.mark.parametrize("cov", O.KERNELS)
+def test_permutation_invariance_and_diagonal(cov):
+  x, y = O.make_task(3, 37, 3, cov)
+  model = O.init_raw_params(3)
+  model["lengthscale"] = np.array([0.3, -0.2, 0.1])
+  v = O.nll_sub_dataset("constant", cov, model, x, y, WF)
+  perm = np.random.default_rng(0).permutation(37)
+  vp = O.nll_sub_dataset("constant", cov, model, x[perm], y[perm], WF)
+  assert abs(v - vp) < 1e-11 * abs(v)
+  k = O.cov_matrix(cov, model, x, warp_func=WF)
+  (sv,) = O.retrieve_params(model, ["signal_variance"], WF)
+  assert np.allclose(np.diag(k), float(sv), rtol=0, atol=1e-15)  # k(x,x) = sigma_f^2
+  assert np.allclose(O.cov_matrix(cov, model, x, warp_func=WF, diag=True),
+                     float(sv))
+  # diag is ignored when vx2 is given (kernel.py:54-58)
+  assert O.cov_matrix(cov, model, x, x[:5], warp_func=WF, diag=True).shape == (37, 5)
+
+
+def test_infinite_lengthscale_gives_rank_one_gram():
+  x = np.random.default_rng(1).random((20, 2))
+  model = {"constant": 0.0, "lengthscale": 1e9, "signal_variance": 2.5,
+           "noise_variance": 0.1}
+  for cov in O.KERNELS:
+    k = O.cov_matrix(cov, model, x)
+    assert np.allclose(k, 2.5, atol=1e-7)
+    s = np.linalg.svd(k, compute_uv=False)
+    assert s[1] < 1e-6 * s[0]
+
+
+def test_task_sum_linearity_across_shards():
+  """What the multi-GPU reduction relies on: [sum nll, sum grad, count] over
+  disjoint task shards add up to the single-process sums."""
+  d = 2
+  ds = O.make_dataset(7, 15, d, "matern52")
+  model = O.init_raw_params(d)
+  def sums(keys):
+    tot, g = 0.0, np.zeros(3 + d)
+    for k in keys:
+      v, gr = O.nll_and_grad_sub_dataset("constant", "matern52", model, *ds[k],
+                                         warp_func=WF)
+      tot += v
+      g += H.grad_vec(gr, d)
+    return tot, g
+  full = sums(range(7))
+  parts = [sums([k for k in range(7) if k % 3 == r]) for r in range(3)]
+  assert abs(sum(p[0] for p in parts) - full[0]) < 1e-12 * abs(full[0])
+  assert H.rel(sum(p[1] for p in parts), full[1]) < 1e-12
+  v, gr = O.nll_value_and_grad("constant", "matern52", model, ds, WF)
+  assert abs(v - full[0] / 7) < 1e-13 * abs(v)
+  assert H.rel(H.grad_vec(gr, d), full[1] / 7) < 1e-12
