@@ -5,7 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = "/tmp/libhb_stamps.so"
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
                        "-Xcompiler", "-fPIC", "-shared", "-DHB_STAMPS", "-o", so,
-                       os.path.join(ROOT, "hyperbo_b200/csrc/hb_capi.cu")])
+                       *[os.path.join(ROOT, "hyperbo_b200/csrc", u)
+                         for u in ("hb_capi.cu", "hb_f64.cu", "hb_f32.cu")]])
 lib = ctypes.CDLL(so)
 h = ctypes.c_void_p()
 assert lib.hb_create(ctypes.byref(h), 0, 0) == 0
