@@ -62,3 +62,20 @@ def default_mask(d, mean="constant"):
 def rel(a, b):
   a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
   return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def load_kat():
+  """mpmath (60-digit) known-answer cases (tests/golden/make_mpmath_kat.py --
+  generated WITHOUT importing oracle/)."""
+  import json
+  with open(os.path.join(GOLDEN_DIR, "kat_mpmath.json")) as fh:
+    cases = json.load(fh)["cases"]
+  for c in cases:
+    c["dataset"] = {t: (np.asarray(x, dtype=np.float64).reshape(-1, c["d"]),
+                        np.asarray(y, dtype=np.float64).reshape(-1, 1))
+                    for t, (x, y) in enumerate(zip(c["x"], c["y"]))}
+    c["raw"] = np.asarray(c["raw"], dtype=np.float64)
+    c["xq"] = np.asarray(c["xq"], dtype=np.float64).reshape(-1, c["d"])
+    for k in ("nll_task", "grad", "alpha0", "mu", "var", "ei", "pi", "ucb"):
+      c[k] = np.asarray(c[k], dtype=np.float64)
+  return cases

@@ -300,3 +300,34 @@ def test_tied_scalar_lengthscale_adam(eng):
   raw = tr.raw.cpu().numpy()
   assert raw[3] == raw[4] == raw[5]
   assert abs(raw[3] - float(ref_model["lengthscale"])) < 1e-9
+
+
+# ---- CUDA path vs the 60-digit mpmath known answers (generated without the
+# oracle: tests/golden/make_mpmath_kat.py)
+@pytest.mark.parametrize("case", H.load_kat(), ids=lambda c: "kat%d_%s_%s_%s" % (
+    c["id"], c["cov"], c["mean"], "warp" if c["warped"] else "raw"))
+def test_cuda_matches_mpmath_known_answers(eng, case):
+  c = case
+  d, T = c["d"], len(c["ns"])
+  kid, mid = _ids(c["cov"], c["mean"])
+  mask = H.default_mask(d) if c["warped"] else 0
+  ds = _pack(eng, c["dataset"])
+  _, alpha, nll, info = eng.factorize(kid, mid, ds, c["raw"], mask)
+  assert info.tolist() == [0] * T
+  assert H.rel(nll.cpu().numpy(), c["nll_task"]) < TOL_NLL
+  assert H.rel(alpha[:c["ns"][0]].cpu().numpy(), c["alpha0"]) < TOL_FACT
+  sums = eng.nll_grad(kid, mid, ds, c["raw"], mask).cpu().numpy()
+  assert abs(sums[0] / T - c["mean_nll"]) < TOL_NLL * abs(c["mean_nll"])
+  assert H.rel(sums[1:-1] / T, c["grad"]) < TOL_GRAD
+  x0, y0 = c["dataset"][0]
+  cache, _, kinvy, _, _ = eng.build_predictor(kid, mid, x0, y0, c["raw"], mask)
+  scale = T / (T - 1.0) if T > 1 else 1.0
+  target = float(np.max(y0))
+  for acq_id, key, param in ((1, "ei", target), (2, "pi", target + 0.1),
+                             (3, "ucb", 3.0)):
+    mu, var, acq = eng.predict(kid, mid, eng.tensor(x0), cache, c["raw"], mask,
+                               c["xq"], noise_flag=1.0, var_scale=scale,
+                               acq_id=acq_id, acq_param=param)
+    assert H.rel(mu.cpu().numpy().ravel(), c["mu"]) < TOL_PRED
+    assert H.rel(var.cpu().numpy().ravel(), c["var"]) < TOL_PRED
+    assert H.rel(acq.cpu().numpy().ravel(), c[key]) < TOL_PRED

@@ -327,3 +327,35 @@ def test_task_sum_linearity_across_shards():
   v, gr = O.nll_value_and_grad("constant", "matern52", model, ds, WF)
   assert abs(v - full[0] / 7) < 1e-13 * abs(v)
   assert H.rel(H.grad_vec(gr, d), full[1] / 7) < 1e-12
+
+
+# ---- independent pin: 60-digit mpmath evaluation of the reference formulas
+# (tests/golden/make_mpmath_kat.py does not import oracle/)
+KAT = H.load_kat()
+
+
+@pytest.mark.parametrize("case", KAT, ids=lambda c: "kat%d_%s_%s_%s" % (
+    c["id"], c["cov"], c["mean"], "warp" if c["warped"] else "raw"))
+def test_oracle_matches_mpmath_known_answers(case):
+  c = case
+  wf = O.DEFAULT_WARP_FUNC if c["warped"] else None
+  model = H.model_from_raw(c["raw"], c["d"], c["mean"])
+  ds = c["dataset"]
+  val, grad = O.nll_value_and_grad(c["mean"], c["cov"], model, ds, wf)
+  assert abs(val - c["mean_nll"]) <= 1e-12 * abs(c["mean_nll"])
+  for t, (x, y) in ds.items():
+    v = O.nll_sub_dataset(c["mean"], c["cov"], model, x, y, wf)
+    assert abs(v - c["nll_task"][t]) <= 1e-12 * abs(c["nll_task"][t])
+  g = H.grad_vec(grad, c["d"])
+  if c["mean"] == "zero":
+    g[0] = 0.0
+  assert H.rel(g, c["grad"]) < 1e-10
+  mu, var = O.gp_predict(c["mean"], c["cov"], model, ds, c["xq"], 0, wf)
+  assert H.rel(np.ravel(mu), c["mu"]) < 1e-11
+  assert H.rel(np.ravel(var), c["var"]) < 1e-9
+  for name in ("ei", "pi", "ucb"):
+    a = O.acquisition(name, c["mean"], c["cov"], model, ds, 0, c["xq"], wf)
+    assert H.rel(np.ravel(a), c[name]) < 1e-8, name
+  _, kinvy, _ = O.solve_gp_linear_system(c["mean"], c["cov"], model, ds[0][0],
+                                         ds[0][1], wf)
+  assert H.rel(np.ravel(kinvy), c["alpha0"]) < 1e-9
