@@ -61,6 +61,8 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   h->device = device;
   h->dtype = dtype;
   if (const char* e = getenv("HB_PRE")) h->pre_override = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("HB_FUSED")) h->fused = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("HB_FUSED_GRID")) h->fused_grid = atoi(e);
   {
     cudaDeviceProp prop;
     // CTA slots of one wave (2 resident CTAs per SM in fp64, 3 in fp32)
@@ -78,11 +80,14 @@ int hb_destroy(hb_handle_t h) {
   Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                 &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                 &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
-                &h->vpart, &h->pcache, &h->pre};
+                &h->vpart, &h->pcache, &h->pre, &h->sync, &h->apart};
   for (auto* b : all)
     if (b->p) cudaFree(b->p);
-  for (auto& p : h->plans)
+  for (auto& p : h->plans) {
     if (p.tasks_d) cudaFree(p.tasks_d);
+    for (void* it : p.items_d)
+      if (it) cudaFree(it);
+  }
   delete h;
   return HB_OK;
 }
@@ -90,6 +95,7 @@ int hb_destroy(hb_handle_t h) {
 const char* hb_last_error(hb_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 int64_t hb_launch_count(hb_handle_t h) { return h ? h->launches : 0; }
 int64_t hb_workspace_bytes(hb_handle_t h) { return h ? (int64_t)total_ws(h) : 0; }
+int64_t hb_generation(hb_handle_t h) { return h ? (int64_t)h->generation : -1; }
 
 #ifdef HB_STAMPS
 int hb_debug_stamps(hb_handle_t h, long long* host_out, int64_t n) {

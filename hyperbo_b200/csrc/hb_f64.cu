@@ -12,6 +12,7 @@ using Real2 = double2;
 __device__ __forceinline__ Real2 make_real2(Real a, Real b) { return make_double2(a, b); }
 #include "hb_device.inc"
 #include "hb_kernels.inc"
+#include "hb_fused.inc"
 #include "hb_host.inc"
 }  // namespace f64
 }  // namespace hb

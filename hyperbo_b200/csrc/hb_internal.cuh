@@ -4,6 +4,7 @@
 // engine precision (hb_f64.cu / hb_f32.cu, in parallel); hb_capi.cu holds the
 // extern "C" entry points and dispatches on the handle's dtype.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,11 @@ struct Plan {
   long long total_tiles = 0, total_blocks = 0, sum_n = 0, chol_elems = 0;
   uint64_t stamp = 0;
   bool uploaded = false;
+  // work-item lists of the persistent kernel (hb_fused.inc), built lazily per
+  // variant: 0 = factor only, 1 = + triangular inverse, 2 = + K~^{-1}/gradient
+  void* items_d[3] = {nullptr, nullptr, nullptr};
+  size_t items_cap[3] = {0, 0, 0};
+  int nitems[3] = {-1, -1, -1};
 };
 
 constexpr int NPLAN = 4;
@@ -47,8 +53,12 @@ struct hb_handle_s {
   uint64_t clock = 0;
   hb::host::Plan plans[hb::host::NPLAN];
   hb::host::Buf theta, Lt, Mt, Wt, zz, z, alpha, logdet, asum, nll_task, gpart, gtask, info, bad,
-      sums, kst, mupart, vpart, pcache, stamps, pre;
+      sums, kst, mupart, vpart, pcache, stamps, pre, sync, apart;
   bool attr_set = false;
+  int sm_count = 0;
+  int fused = 1;               // HB_FUSED env: 0 = the launch-per-column path
+  int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel
+  uint64_t generation = 0;     // bumped whenever a workspace buffer or plan moves
   int pre_override = -1;       // HB_PRE env: force the k_step pre roles off / on
   long long pre_cta_limit = 0; // pre roles on when T * (nblk_max + 1) <= this
   int smem_d = -1;
@@ -75,6 +85,7 @@ inline int fail(hb_handle_t h, int code, const char* msg) {
 
 inline int ensure(hb_handle_t h, Buf& b, size_t bytes) {
   if (bytes <= b.cap) return HB_OK;
+  ++h->generation;  // captured CUDA graphs hold the old pointer
   if (b.p) HB_CUDA(cudaFree(b.p));
   b.p = nullptr;
   b.cap = 0;
@@ -88,10 +99,13 @@ inline size_t total_ws(hb_handle_t h) {
   const Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                       &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                       &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
-                      &h->vpart, &h->pcache, &h->pre};
+                      &h->vpart, &h->pcache, &h->pre, &h->sync, &h->apart};
   size_t s = 0;
   for (auto* b : all) s += b->cap;
-  for (auto& p : h->plans) s += p.tasks_cap;
+  for (auto& p : h->plans) {
+    s += p.tasks_cap;
+    for (size_t c : p.items_cap) s += c;
+  }
   return s;
 }
 
@@ -110,7 +124,9 @@ inline int get_plan(hb_handle_t h, int T, const int64_t* offs, int d, cudaStream
     if (p.stamp < lru->stamp) lru = &p;
   }
   Plan& p = *lru;
+  if (p.uploaded) ++h->generation;  // an evicted plan may be baked into a graph
   p.uploaded = false;
+  for (int& n : p.nitems) n = -1;
   p.T = T;
   p.d = d;
   p.offs.assign(offs, offs + T + 1);
@@ -138,6 +154,7 @@ inline int get_plan(hb_handle_t h, int T, const int64_t* offs, int d, cudaStream
   p.chol_elems = chol;
   const size_t bytes = sizeof(TaskDesc) * (size_t)std::max(T, 1);
   if (bytes > p.tasks_cap) {
+    ++h->generation;
     if (p.tasks_d) HB_CUDA(cudaFree(p.tasks_d));
     p.tasks_d = nullptr;
     HB_CUDA(cudaMalloc(&p.tasks_d, bytes));

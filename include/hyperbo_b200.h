@@ -78,6 +78,11 @@ const char* hb_version(void);
 int64_t hb_launch_count(hb_handle_t h);
 /* Bytes of device workspace currently held. */
 int64_t hb_workspace_bytes(hb_handle_t h);
+/* Generation counter of the handle's device state: bumped whenever a workspace
+ * buffer is re-allocated or a cached plan is evicted.  A caller that captured
+ * engine calls into a CUDA graph must re-capture when it changes (the graph
+ * holds raw workspace pointers). */
+int64_t hb_generation(hb_handle_t h);
 /* Per-kernel timing for bench.py's roofline: when enabled, CUDA events are
  * recorded on the caller's stream around each section of
  * hb_nll_grad_batched / hb_factorize_batched:
