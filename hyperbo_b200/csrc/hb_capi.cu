@@ -28,8 +28,8 @@ using namespace hb::host;
   int acquisition_impl(hb_handle_t, int, double, int64_t, const void*,          \
                        const void*, void*, void*);
 namespace hb {
-namespace f64 { HB_IMPL_PROTOTYPES }
-namespace f32 { HB_IMPL_PROTOTYPES }
+namespace f64 { HB_IMPL_PROTOTYPES int fused_timeout_impl(); }
+namespace f32 { HB_IMPL_PROTOTYPES int fused_timeout_impl(); }
 }  // namespace hb
 #undef HB_IMPL_PROTOTYPES
 
@@ -63,6 +63,8 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   if (const char* e = getenv("HB_PRE")) h->pre_override = atoi(e) ? 1 : 0;
   if (const char* e = getenv("HB_FUSED")) h->fused = atoi(e) ? 1 : 0;
   if (const char* e = getenv("HB_FUSED_GRID")) h->fused_grid = atoi(e);
+  if (const char* e = getenv("HB_FUSED_SKEW")) h->fused_skew = atof(e);
+  if (const char* e = getenv("HB_FUSED_GROUPS")) h->fused_groups = atoi(e);
   {
     cudaDeviceProp prop;
     // CTA slots of one wave (2 resident CTAs per SM in fp64, 3 in fp32)
@@ -96,6 +98,10 @@ const char* hb_last_error(hb_handle_t h) { return h ? h->err.c_str() : "null han
 int64_t hb_launch_count(hb_handle_t h) { return h ? h->launches : 0; }
 int64_t hb_workspace_bytes(hb_handle_t h) { return h ? (int64_t)total_ws(h) : 0; }
 int64_t hb_generation(hb_handle_t h) { return h ? (int64_t)h->generation : -1; }
+int hb_debug_fused_timeout(hb_handle_t h) {
+  if (!h) return -1;
+  return h->dtype == HB_F64 ? hb::f64::fused_timeout_impl() : hb::f32::fused_timeout_impl();
+}
 
 #ifdef HB_STAMPS
 int hb_debug_stamps(hb_handle_t h, long long* host_out, int64_t n) {

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace hb {
 
@@ -43,6 +44,12 @@ __host__ __device__ __forceinline__ int elem_off(int r, int c) {
   return ((((r >> 3) << 4) + (c >> 2)) << 5) + ((r & 7) << 2) + (c & 3);
 }
 
+#ifdef HB_FUSED_DEBUG
+__device__ int g_dbg[8 * 1024];
+#define HB_DBG_AT(n_) do { if (threadIdx.x == 0) g_dbg[blockIdx.x * 8 + 2] = (n_); } while (0)
+#else
+#define HB_DBG_AT(n_)
+#endif
 // ------------------------------------------------------------------ PTX ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -64,7 +71,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   const uint32_t a = smem_u32(bar);
+#ifdef HB_FUSED_DEBUG
+  unsigned long long spins_ = 0;
+#endif
   while (!done) {
+#ifdef HB_FUSED_DEBUG
+    if (++spins_ > (1ull << 26)) {
+      if ((threadIdx.x & 31) <= 1)
+        printf("mbarrier timeout: block %d thread %d bar %u parity %u | item %d desc %x t0-at %d\n",
+               blockIdx.x, threadIdx.x, a, parity, g_dbg[blockIdx.x * 8], g_dbg[blockIdx.x * 8 + 1],
+               g_dbg[blockIdx.x * 8 + 2]);
+      break;
+    }
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -38,6 +38,8 @@ struct Plan {
   void* items_d[3] = {nullptr, nullptr, nullptr};
   size_t items_cap[3] = {0, 0, 0};
   int nitems[3] = {-1, -1, -1};
+  int ngroups[3] = {1, 1, 1};
+  size_t gofs_off[3] = {0, 0, 0};
 };
 
 constexpr int NPLAN = 4;
@@ -58,6 +60,9 @@ struct hb_handle_s {
   int sm_count = 0;
   int fused = 1;               // HB_FUSED env: 0 = the launch-per-column path
   int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel
+  double fused_skew = 0.0;     // HB_FUSED_SKEW env: task skew of the item order
+  int fused_groups = 0;        // HB_FUSED_GROUPS env: work queues (0 = automatic)
+  int fused_per_sm[2][hb::MAX_DIM + 1] = {};  // cached occupancy per (mapping, d)
   uint64_t generation = 0;     // bumped whenever a workspace buffer or plan moves
   int pre_override = -1;       // HB_PRE env: force the k_step pre roles off / on
   long long pre_cta_limit = 0; // pre roles on when T * (nblk_max + 1) <= this

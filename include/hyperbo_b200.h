@@ -83,6 +83,9 @@ int64_t hb_workspace_bytes(hb_handle_t h);
  * engine calls into a CUDA graph must re-capture when it changes (the graph
  * holds raw workspace pointers). */
 int64_t hb_generation(hb_handle_t h);
+/* Debug: synchronises the device and returns 1 if a work item of the persistent
+ * kernel ever gave up waiting for a dependency (a scheduling bug), else 0. */
+int hb_debug_fused_timeout(hb_handle_t h);
 /* Per-kernel timing for bench.py's roofline: when enabled, CUDA events are
  * recorded on the caller's stream around each section of
  * hb_nll_grad_batched / hb_factorize_batched:
