@@ -65,6 +65,7 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   if (const char* e = getenv("HB_FUSED_GRID")) h->fused_grid = atoi(e);
   if (const char* e = getenv("HB_FUSED_SKEW")) h->fused_skew = atof(e);
   if (const char* e = getenv("HB_FUSED_GROUPS")) h->fused_groups = atoi(e);
+  if (const char* e = getenv("HB_FUSED_VT_DIAG")) h->fused_vt_diag = atof(e);
   {
     cudaDeviceProp prop;
     // CTA slots of one wave (2 resident CTAs per SM in fp64, 3 in fp32)

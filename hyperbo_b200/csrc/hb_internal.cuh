@@ -62,6 +62,7 @@ struct hb_handle_s {
   int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel
   double fused_skew = 0.0;     // HB_FUSED_SKEW env: task skew of the item order
   int fused_groups = 0;        // HB_FUSED_GROUPS env: work queues (0 = automatic)
+  double fused_vt_diag = 0.4;  // HB_FUSED_VT_DIAG env: queue position of DIAG(j+1)
   int fused_per_sm[2][hb::MAX_DIM + 1] = {};  // cached occupancy per (mapping, d)
   uint64_t generation = 0;     // bumped whenever a workspace buffer or plan moves
   int pre_override = -1;       // HB_PRE env: force the k_step pre roles off / on

@@ -26,7 +26,7 @@ def P(t): return ctypes.c_void_p(t.data_ptr())
 for _ in range(3):
   assert lib.hb_nll_grad_batched(h, 0, 1, T, offs, d, P(x), P(y), P(raw), ctypes.c_uint64(mask), P(sums), None, None, None) == 0
 torch.cuda.synchronize()
-nitems = T * (8 + 28 + 28 + 36)
+nitems = T * (8 + 28 + 28 + 36 + 1)
 buf = np.zeros((nitems, 8), dtype=np.int64)
 lib.hb_debug_stamps(h, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), ctypes.c_int64(buf.size))
 if len(sys.argv) > 2:
