@@ -28,8 +28,13 @@ using namespace hb::host;
   int acquisition_impl(hb_handle_t, int, double, int64_t, const void*,          \
                        const void*, void*, void*);
 namespace hb {
-namespace f64 { HB_IMPL_PROTOTYPES int fused_timeout_impl(); }
-namespace f32 { HB_IMPL_PROTOTYPES int fused_timeout_impl(); }
+#define HB_COMM_PROTOTYPES                                                      \
+  int fused_timeout_impl();                                                     \
+  int allreduce_impl(hb_handle_t, void*, int, void*);                           \
+  int allreduce_adam_impl(hb_handle_t, int, void*, void*, void*, void*, void*,  \
+                          void*, double, double, double, double, int, void*);
+namespace f64 { HB_IMPL_PROTOTYPES HB_COMM_PROTOTYPES }
+namespace f32 { HB_IMPL_PROTOTYPES HB_COMM_PROTOTYPES }
 }  // namespace hb
 #undef HB_IMPL_PROTOTYPES
 
@@ -78,8 +83,22 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   return HB_OK;
 }
 
+static void comm_release(hb_handle_t h) {
+  for (int r = 0; r < (int)h->xbuf_peers.size(); ++r)
+    if (h->xbuf_peers[r] && r != h->comm_rank) cudaIpcCloseMemHandle(h->xbuf_peers[r]);
+  h->xbuf_peers.clear();
+  if (h->xbuf_peers_d) cudaFree(h->xbuf_peers_d);
+  if (h->comm_step_d) cudaFree(h->comm_step_d);
+  h->xbuf_peers_d = nullptr;
+  h->comm_step_d = nullptr;
+  h->comm_world = 0;
+  h->comm_rank = -1;
+}
+
 int hb_destroy(hb_handle_t h) {
   if (!h) return HB_ERR_BAD_ARG;
+  comm_release(h);
+  if (h->xbuf_own) cudaFree(h->xbuf_own);
   Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                 &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                 &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
@@ -138,6 +157,63 @@ int hb_profile_read(hb_handle_t h, double* ms_out, int64_t* count_out) {
     count_out[s] = (int64_t)h->prof_ev[s].size();
   }
   return HB_OK;
+}
+
+// ---- peer-memory all-reduce (SURVEY 8b hb_allreduce, 8e) -------------------
+int hb_comm_export(hb_handle_t h, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return HB_ERR_BAD_ARG;
+  HB_CUDA(cudaSetDevice(h->device));
+  if (!h->xbuf_own) {
+    HB_CUDA(cudaMalloc(&h->xbuf_own, HB_XBUF_BYTES));
+    HB_CUDA(cudaMemset(h->xbuf_own, 0, HB_XBUF_BYTES));
+    HB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hd;
+  HB_CUDA(cudaIpcGetMemHandle(&hd, h->xbuf_own));
+  static_assert(sizeof(cudaIpcMemHandle_t) == HB_IPC_HANDLE_BYTES, "ipc handle size");
+  std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+  return HB_OK;
+}
+
+int hb_comm_import(hb_handle_t h, int rank, int world, const void* ipc_handles) {
+  if (!h || !ipc_handles || world < 1 || world > HB_XCHG_MAX || rank < 0 || rank >= world)
+    return fail(h, HB_ERR_BAD_ARG, "comm args");
+  if (!h->xbuf_own) return fail(h, HB_ERR_BAD_ARG, "hb_comm_export first");
+  HB_CUDA(cudaSetDevice(h->device));
+  comm_release(h);
+  h->comm_rank = rank;
+  h->xbuf_peers.assign(world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->xbuf_peers[r] = h->xbuf_own;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, (const char*)ipc_handles + (size_t)r * sizeof(hd), sizeof(hd));
+    HB_CUDA(cudaIpcOpenMemHandle(&h->xbuf_peers[r], hd, cudaIpcMemLazyEnablePeerAccess));
+  }
+  HB_CUDA(cudaMemset(h->xbuf_own, 0, HB_XBUF_BYTES));
+  HB_CUDA(cudaMalloc((void**)&h->xbuf_peers_d, sizeof(void*) * world));
+  HB_CUDA(cudaMemcpy(h->xbuf_peers_d, h->xbuf_peers.data(), sizeof(void*) * world,
+                     cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMalloc((void**)&h->comm_step_d, sizeof(unsigned)));
+  HB_CUDA(cudaMemset(h->comm_step_d, 0, sizeof(unsigned)));
+  HB_CUDA(cudaDeviceSynchronize());
+  h->comm_world = world;
+  ++h->generation;
+  return HB_OK;
+}
+
+int hb_allreduce(hb_handle_t h, void* buf, int count, void* stream) {
+  HB_DISPATCH(allreduce_impl, h, buf, count, stream);
+}
+
+int hb_allreduce_adam_step(hb_handle_t h, int P_, void* raw, void* m, void* v,
+                           void* accepted, void* sums, void* scalars_io, double lr,
+                           double b1, double b2, double eps, int tie_lengthscale,
+                           void* stream) {
+  HB_DISPATCH(allreduce_adam_impl, h, P_, raw, m, v, accepted, sums, scalars_io, lr,
+              b1, b2, eps, tie_lengthscale, stream);
 }
 
 int hb_kernel_matrix(hb_handle_t h, int kernel_id, const void* X1, int64_t n1,

@@ -223,6 +223,8 @@ constexpr int TH_SIZE = 128;
 constexpr double JITTER = 1e-6;    // basics/linalg.py:42
 constexpr double EPS_WARP = 1e-10; // gp_utils/utils.py:28,73
 constexpr int GP_STRIDE = 2 + MAX_DIM;  // [sv, nv, ls...]
+constexpr int HB_XCHG_MAX = 64;         // scalars per peer-memory all-reduce
+constexpr int HB_XBUF_BYTES = 128 + 2 * HB_XCHG_MAX * 8;
 constexpr int LPT_GROUP_MAX = 256;      // tasks per launch-order group (<= T)
 __host__ __device__ inline int xstride(int d) { return d | 1; }
 

@@ -68,6 +68,13 @@ struct hb_handle_s {
   int pre_override = -1;       // HB_PRE env: force the k_step pre roles off / on
   long long pre_cta_limit = 0; // pre roles on when T * (nblk_max + 1) <= this
   int smem_d = -1;
+  // peer-memory all-reduce (hb_comm_*): own exchange buffer, the ranks' buffers
+  // mapped with CUDA IPC, device array of their addresses, device step counter
+  int comm_rank = -1, comm_world = 0;
+  void* xbuf_own = nullptr;
+  std::vector<void*> xbuf_peers;     // [world]; entry `rank` == xbuf_own
+  void** xbuf_peers_d = nullptr;
+  unsigned* comm_step_d = nullptr;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[HB_PROFILE_SECTIONS];
 };

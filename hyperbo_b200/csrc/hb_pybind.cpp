@@ -120,6 +120,35 @@ PYBIND11_MODULE(_C, m) {
                                   P(stream)),
                      "hb_adam_step");
            })
+      .def("generation", [](Handle& s) { return hb_generation(s.h); })
+      .def("debug_fused_timeout", [](Handle& s) { return hb_debug_fused_timeout(s.h); })
+      .def("comm_export",
+           [](Handle& s) {
+             char buf[HB_IPC_HANDLE_BYTES];
+             s.check(hb_comm_export(s.h, buf), "hb_comm_export");
+             return py::bytes(buf, HB_IPC_HANDLE_BYTES);
+           })
+      .def("comm_import",
+           [](Handle& s, int rank, int world, const std::string& handles) {
+             if ((int)handles.size() != world * HB_IPC_HANDLE_BYTES)
+               throw std::invalid_argument("comm_import: handles size");
+             s.check(hb_comm_import(s.h, rank, world, handles.data()), "hb_comm_import");
+           })
+      .def("allreduce",
+           [](Handle& s, ptr_t buf, int count, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_allreduce(s.h, P(buf), count, P(stream)), "hb_allreduce");
+           })
+      .def("allreduce_adam_step",
+           [](Handle& s, int np, ptr_t raw, ptr_t mm, ptr_t vv, ptr_t accepted,
+              ptr_t sums, ptr_t scal, double lr, double b1, double b2, double eps,
+              int tie_ls, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_allreduce_adam_step(s.h, np, P(raw), P(mm), P(vv), P(accepted),
+                                            P(sums), P(scal), lr, b1, b2, eps, tie_ls,
+                                            P(stream)),
+                     "hb_allreduce_adam_step");
+           })
       .def("build_predictor",
            [](Handle& s, int kernel_id, int mean_id, int64_t n, int d, ptr_t X,
               ptr_t y, ptr_t raw, uint64_t mask, ptr_t cache, ptr_t chol,

@@ -232,6 +232,59 @@ class Engine:
       return sums_out, nll_task[:T]
     return sums_out
 
+  def generation(self) -> int:
+    """Bumped whenever a workspace buffer / cached plan of the handle moves:
+    CUDA graphs that captured engine calls must be re-captured then."""
+    return int(self.h.generation())
+
+  # ---- peer-memory all-reduce (hb_comm_*, SURVEY 8e) -----------------------
+  def comm_init(self) -> bool:
+    """Set up the NVLink peer-memory all-reduce between the ranks of the default
+    torch.distributed group (one process per GPU of ONE node).  Returns False
+    when it cannot be used (single rank, no CUDA IPC / peer access); the caller
+    then falls back to torch.distributed.all_reduce."""
+    import torch.distributed as dist
+    if getattr(self, "_comm_ready", None) is not None:
+      return self._comm_ready
+    self._comm_ready = False
+    if getattr(self, "h", None) is None or self.device.type != "cuda":
+      return False  # (an engine without a C-ABI handle: the CPU test double)
+    if not (dist.is_available() and dist.is_initialized()):
+      return False
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world < 2 or world > 64:
+      return False
+    ok = 1
+    try:
+      handle = self.h.comm_export()
+    except RuntimeError:
+      handle, ok = b"\0" * 64, 0
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ok, handle))
+    if all(g[0] for g in gathered):
+      try:
+        self.h.comm_import(rank, world, b"".join(g[1] for g in gathered))
+      except RuntimeError:
+        ok = 0
+    else:
+      ok = 0
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)  # (also the barrier hb_comm_import needs)
+    self._comm_ready = all(flags)
+    return self._comm_ready
+
+  def allreduce(self, buf: torch.Tensor):
+    """In-place deterministic all-reduce(sum) of <= 64 scalars (hb_allreduce)."""
+    self.h.allreduce(buf.data_ptr(), int(buf.numel()), self._stream())
+
+  def allreduce_adam_step(self, P: int, raw, m, v, accepted, sums, scal, lr,
+                          b1=0.9, b2=0.999, eps=1e-8, tie_lengthscale=False):
+    self.h.allreduce_adam_step(P, raw.data_ptr(), m.data_ptr(), v.data_ptr(),
+                               accepted.data_ptr(), sums.data_ptr(),
+                               scal.data_ptr(), float(lr), float(b1), float(b2),
+                               float(eps), int(bool(tie_lengthscale)),
+                               self._stream())
+
   def adam_step(self, P: int, raw, m, v, accepted, sums, scal, lr, b1=0.9,
                 b2=0.999, eps=1e-8, tie_lengthscale=False):
     self.h.adam_step(P, raw.data_ptr(), m.data_ptr(), v.data_ptr(),

@@ -74,6 +74,7 @@ class AdamTrainer:
     self.allreduce = allreduce
     self.tie_lengthscale = tie_lengthscale
     self._graphs = {}
+    self._graph_gen = -1
     self._graph_failed = False
     self._copy_stream = None
     self._host_bufs = None
@@ -81,6 +82,14 @@ class AdamTrainer:
     self._loss_pin = None
     self._loss_evt = None
     self._nsteps = 0
+
+  def _peer_comm(self) -> bool:
+    """True when the all-reduce runs in the engine (NVLink peer memory, fused
+    with the Adam update: hb_allreduce_adam_step) instead of in NCCL."""
+    if not self.allreduce or os.environ.get("HB_PEER_ALLREDUCE", "1") == "0":
+      return False
+    init = getattr(self.eng, "comm_init", None)
+    return bool(init and init())
 
   def _enqueue(self, ds):
     if isinstance(ds, obj.ObjectiveProgram):
@@ -91,16 +100,33 @@ class AdamTrainer:
       self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
                         sums_out=self.sums)
       if self.allreduce:
+        if self._peer_comm():
+          # ONE kernel: exchange of the P+2 partial sums over peer memory, the
+          # rank-ordered sum and the Adam update
+          self.eng.allreduce_adam_step(self.P, self.raw, self.m, self.v,
+                                       self.accepted, self.sums, self.scal,
+                                       self.lr, self.b1, self.b2, self.eps,
+                                       self.tie_lengthscale)
+          return
         import torch.distributed as dist
         dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)
     self.eng.adam_step(self.P, self.raw, self.m, self.v, self.accepted,
                        self.sums, self.scal, self.lr, self.b1, self.b2,
                        self.eps, self.tie_lengthscale)
 
-  def _graphed(self, key, fn):
+  def _graphed(self, key, ds, fn):
     """Capture fn() once into a CUDA graph (after an eager warm-up that sizes
-    the engine workspace) and replay it afterwards."""
-    if key not in self._graphs:
+    the engine workspace) and replay it afterwards.  A graph holds raw engine
+    workspace pointers and the batch's device buffers: it is dropped when the
+    handle's generation changes (a buffer was re-allocated / a plan evicted,
+    e.g. by a callback that ran predict on a larger task) and it is only
+    replayed for the very same batch object."""
+    gen = self.eng.generation() if hasattr(self.eng, "generation") else 0
+    if gen != self._graph_gen:
+      self._graphs = {}
+      self._graph_gen = gen
+    ent = self._graphs.get(key)
+    if ent is None or ent[1] is not ds:
       tensors = (self.raw, self.m, self.v, self.accepted, self.scal)
       state = [t.clone() for t in tensors]
       s = torch.cuda.Stream(device=self.eng.device)
@@ -111,6 +137,8 @@ class AdamTrainer:
       torch.cuda.synchronize(self.eng.device)
       for t, c in zip(tensors, state):
         t.copy_(c)
+      if hasattr(self.eng, "generation"):
+        self._graph_gen = self.eng.generation()  # (the warm-up may have grown it)
       g = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g):
         fn()
@@ -118,22 +146,25 @@ class AdamTrainer:
         t.copy_(c)
       if len(self._graphs) >= 4:  # bounded cache (a new batch object per step)
         self._graphs.pop(next(iter(self._graphs)))
-      self._graphs[key] = g
-    self._graphs[key].replay()
+      ent = (g, ds)  # (keeps the batch alive as long as its graph)
+      self._graphs[key] = ent
+    ent[0].replay()
 
   def _graph_ok(self, use_graph):
-    # Multi-GPU steps stay eager: capturing the NCCL all-reduce into the graph
-    # hung on the 2-GPU test box (round 1), so it is opt-in (HB_GRAPH_NCCL=1).
     if not use_graph or self._graph_failed or self.eng.device.type != "cuda":
       return False
-    return not self.allreduce or os.environ.get("HB_GRAPH_NCCL", "0") == "1"
+    # several ranks: the whole step (incl. the peer-memory all-reduce + Adam
+    # kernel) is one graph; with the NCCL fallback the collective stays eager
+    # (capturing it hung on the round-1 test box; HB_GRAPH_NCCL=1 opts in)
+    return (not self.allreduce or self._peer_comm() or
+            os.environ.get("HB_GRAPH_NCCL", "0") == "1")
 
-  def _run(self, key, fn, use_graph, force=False):
+  def _run(self, key, ds, fn, use_graph, force=False):
     if not (force or self._graph_ok(use_graph)):
       fn()
       return
     try:
-      self._graphed(key, fn)
+      self._graphed(key, ds, fn)
     except RuntimeError as e:  # capture not possible here: stay eager
       logging.warning("CUDA-graph capture failed (%s); using eager launches", e)
       self._graph_failed = True
@@ -144,14 +175,12 @@ class AdamTrainer:
   def step(self, ds, use_graph=False):
     """Enqueue one optimiser step on the current stream."""
     if (use_graph and self.allreduce and not self._graph_failed and
-        self.eng.device.type == "cuda" and
+        self.eng.device.type == "cuda" and not self._peer_comm() and
         not isinstance(ds, obj.ObjectiveProgram) and
         os.environ.get("HB_GRAPH_NCCL", "0") != "1"):
-      # several ranks: the kernel sequence of hb_nll_grad_batched replays from a
-      # CUDA graph (short, dependent launches: the gaps between them matter
-      # most when each rank holds few tasks); the all-reduce and the Adam
-      # kernel stay eager (capturing the NCCL call hung on the test box).
-      self._run(("nll", id(ds)),
+      # NCCL fallback: the kernel sequence of hb_nll_grad_batched replays from a
+      # CUDA graph; the all-reduce and the Adam kernel stay eager.
+      self._run(("nll", id(ds)), ds,
                 lambda: self.eng.nll_grad(self.kid, self.mid, ds, self.raw,
                                           self.mask, sums_out=self.sums),
                 True, force=True)
@@ -161,7 +190,7 @@ class AdamTrainer:
                          self.sums, self.scal, self.lr, self.b1, self.b2,
                          self.eps, self.tie_lengthscale)
       return
-    self._run(("dev", id(ds)), lambda: self._enqueue(ds), use_graph)
+    self._run(("dev", id(ds)), ds, lambda: self._enqueue(ds), use_graph)
 
   def step_from_host(self, ds, x_host: torch.Tensor, y_host: torch.Tensor,
                      use_graph=False):
@@ -258,7 +287,10 @@ def _infer_parameters_quasi_newton(eng, kid, mid, params, dataset, warp_func,
   objective is the engine's batched value-and-gradient."""
   from hyperbo_b200.basics import bfgs as _bfgs
   from hyperbo_b200.basics import lbfgs as _lbfgs
-  batch = next(data_utils.sub_sample_dataset_iterator(key, dataset, batch_size))
+  # only lbfgs sub-samples (gp.py:102-107, "to handle very large sub
+  # datasets"); bfgs optimises the full dataset
+  batch = (next(data_utils.sub_sample_dataset_iterator(key, dataset, batch_size))
+           if method == "lbfgs" else dataset)
   ds = pack(batch)
   any_x = next(iter(dataset.values())).x
   d = int(torch.as_tensor(any_x).shape[1])

@@ -181,6 +181,33 @@ int hb_adam_step(hb_handle_t h, int P, void* raw, void* m, void* v,
                  double b1, double b2, double eps, int tie_lengthscale,
                  void* stream);
 
+/* ---- 8(e): the one exchange step of task-sharded training ---------------- */
+/* The loss is a mean over tasks (gp_utils/objectives.py:178-195), so task shards
+ * on several GPUs (one process per GPU) combine with ONE all-reduce(sum) of the
+ * P+2 partial sums per optimiser step.  These entries do it over NVLink peer
+ * memory inside one small kernel per rank -- no NCCL call, capturable in a CUDA
+ * graph -- and reduce in rank order, so every rank holds bit-identical sums.
+ *
+ *   hb_comm_export : allocates this rank's exchange buffer and writes its CUDA
+ *                    IPC handle (HB_IPC_HANDLE_BYTES bytes) to ipc_handle_out;
+ *   (the caller all-gathers the handles with whatever transport it has,)
+ *   hb_comm_import : maps the peers' buffers; ipc_handles = world consecutive
+ *                    handles in rank order.  Every rank must return from it
+ *                    (barrier) before any rank enqueues an all-reduce.
+ *   hb_allreduce   : buf[0..count) <- sum over ranks, count <= 64, in place;
+ *   hb_allreduce_adam_step : the same on sums[0..P+2) followed by hb_adam_step's
+ *                    update in the same kernel (what gp.infer_parameters needs
+ *                    per step, gp_utils/gp.py:134-144).
+ * Collective: every rank must enqueue the same sequence of these calls. */
+#define HB_IPC_HANDLE_BYTES 64
+int hb_comm_export(hb_handle_t h, void* ipc_handle_out);
+int hb_comm_import(hb_handle_t h, int rank, int world, const void* ipc_handles);
+int hb_allreduce(hb_handle_t h, void* buf, int count, void* stream);
+int hb_allreduce_adam_step(hb_handle_t h, int P, void* raw, void* m, void* v,
+                           void* accepted, void* sums, void* scalars_io, double lr,
+                           double b1, double b2, double eps, int tie_lengthscale,
+                           void* stream);
+
 /* ---- a12/a13: predictor cache, predict, acquisition --------------------- */
 /* Bytes of the opaque predictor cache for n observations (packed L^{-1} tiles,
  * alpha, padded).  */

@@ -1,19 +1,26 @@
-"""World-size-2 gloo test (CPU) of the multi-GPU reduction contract: every rank
-computes [sum nll, sum grad, count] over its round-robin task shard, ONE
-all-reduce(sum) combines them, and the replicated Adam update is identical on
-all ranks.  The per-shard arithmetic comes from the oracle here;
-on GPUs it is hb_nll_grad_batched."""
+"""World-size-2 gloo test (CPU) of the PRODUCT's multi-rank training path:
+gp.infer_parameters on every rank shards the tasks round-robin (gp.shard_tasks),
+each step combines the ranks' [sum nll, sum grad, count] with ONE all-reduce
+(AdamTrainer, the torch.distributed fallback of the engine's peer-memory
+all-reduce) and applies the replicated Adam update.  The engine's
+arithmetic comes from tests/fake_engine.py (the oracle on CPU tensors); the
+result must equal the oracle's single-process Adam loop, and the replicas must
+stay bit-identical.  On GPUs the same host code runs over hb_nll_grad_batched
+and hb_allreduce_adam_step (tests/test_gpu_multirank.py)."""
 import os
 import socket
 
 import numpy as np
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hyperbo_b200.gp_utils import gp
+from hyperbo_b200.basics import definitions as defs
+from hyperbo_b200.gp_utils import gp, kernel, mean, objectives, utils
 from oracle import hyperbo_oracle as O
+from tests import fake_engine
 from tests import helpers as H
+
+D, TASKS, N, STEPS, LR = 2, 5, 12, 3, 1e-2
 
 
 def _free_port():
@@ -24,37 +31,26 @@ def _free_port():
   return p
 
 
-def _shard_sums(model, items, d):
-  tot, gsum = 0.0, np.zeros(3 + d)
-  for _, x, y in items:
-    v, g = O.nll_and_grad_sub_dataset("constant", "squared_exponential", model, x,
-                                      y, O.DEFAULT_WARP_FUNC)
-    tot += v
-    gsum += H.grad_vec(g, d)
-  return np.concatenate([[tot], gsum, [float(len(items))]])
-
-
 def _worker(rank, world, port, out):
   os.environ["MASTER_ADDR"] = "127.0.0.1"
   os.environ["MASTER_PORT"] = str(port)
   dist.init_process_group("gloo", rank=rank, world_size=world)
-  d = 2
-  ds = O.make_dataset(5, 12, d)
-  items = [(k, v[0], v[1]) for k, v in ds.items()]
-  model = O.init_raw_params(d)
-  opt = O.Adam(1e-2)
+  from hyperbo_b200 import engine as _engine
+  eng = fake_engine.FakeEngine()
+  _engine.Engine.get = staticmethod(lambda *a, **k: eng)
+  ds = O.make_dataset(TASKS, N, D)
+  dataset = {k: defs.SubDataset(*v) for k, v in ds.items()}
+  params = defs.GPParams(
+      model=dict(O.init_raw_params(D)),
+      config={"method": "adam", "learning_rate": LR, "max_training_step": STEPS,
+              "batch_size": 1000, "objective": objectives.nll})
   losses = []
-  for _ in range(3):
-    mine = gp.shard_tasks(items, rank, world)
-    sums = torch.from_numpy(_shard_sums(model, mine, d))
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    s = sums.numpy()
-    losses.append(s[0] / s[-1])
-    g = s[1:-1] / s[-1]
-    grads = {"constant": g[0], "signal_variance": g[1], "noise_variance": g[2],
-             "lengthscale": g[3:]}
-    model = opt.update(model, grads)
-  out[rank] = (losses, H.raw_vec(model, d))
+  res = gp.infer_parameters(
+      mean.constant, kernel.squared_exponential, params, dataset,
+      warp_func=utils.DEFAULT_WARP_FUNC, objective=objectives.nll, key=0,
+      callback=lambda i, model, loss: losses.append(float(loss)))
+  out[rank] = (losses, H.raw_vec({k: np.asarray(v, dtype=np.float64)
+                                  for k, v in res.model.items()}, D))
   dist.destroy_process_group()
 
 
@@ -66,10 +62,17 @@ def test_two_rank_sharded_training_matches_single_process():
   l0, p0 = out[0]
   l1, p1 = out[1]
   assert l0 == l1 and np.array_equal(p0, p1)  # replicas stay bit-identical
-  d = 2
-  ds = O.make_dataset(5, 12, d)
+  ds = O.make_dataset(TASKS, N, D)
   ref_model, ref_losses = O.infer_parameters_adam(
-      "constant", "squared_exponential", O.init_raw_params(d), ds,
-      O.DEFAULT_WARP_FUNC, 1e-2, 3, 1000)
-  assert H.rel(l0, ref_losses) < 1e-12
-  assert H.rel(p0, H.raw_vec(ref_model, d)) < 1e-12
+      "constant", "squared_exponential", O.init_raw_params(D), ds,
+      O.DEFAULT_WARP_FUNC, LR, STEPS, 1000)
+  assert len(l0) == STEPS
+  assert H.rel(l0, ref_losses[:STEPS]) < 1e-12
+  assert H.rel(p0, H.raw_vec(ref_model, D)) < 1e-12
+
+
+def test_shard_tasks_is_a_balanced_partition():
+  items = list(range(11))
+  shards = [gp.shard_tasks(items, r, 4) for r in range(4)]
+  assert sorted(sum(shards, [])) == items
+  assert max(map(len, shards)) - min(map(len, shards)) <= 1
