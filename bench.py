@@ -44,15 +44,25 @@ def algorithmic_flops(T, n, d):
   }
 
 
-def synthetic_batch(T, n, d, seed=0):
-  """Synthetic (T x n x d) batch: X ~ U[0,1], y = c* + smooth signal + noise
-  (cheap surrogate of the GP draw of SURVEY 8d, same shapes / conditioning)."""
+def synthetic_batch(T, n, d, seed=0, tasks=None):
+  """SURVEY.md 8(d) recipe (bo_utils/data.py:720-775 + gp.py:230-239): per task
+  t, X_t ~ U[0,1]^{n x d} (PCG64 seed 1000+t) and y_t = c* + chol(K*(X_t) +
+  (sigma_n*^2 + 1e-6) I) z, z ~ N(0, I) (seed 2000+t): ONE draw from the
+  ground-truth GP (SE kernel, c* = 5, l* = 1, sigma_f*^2 = 1, sigma_n*^2 = 0.01,
+  used un-warped as in gp_test.py:64-70)."""
   import numpy as np
-  rng = np.random.Generator(np.random.PCG64(seed))
-  x = rng.random((T, n, d))
-  y = 5.0 + np.sum(np.sin(2 * np.pi * x[..., :2]), axis=-1, keepdims=True) \
-      + 0.1 * rng.standard_normal((T, n, 1))
-  return x, y
+  tasks = range(T) if tasks is None else tasks
+  xs, ys = [], []
+  for t in tasks:
+    x = np.random.Generator(np.random.PCG64(1000 + t + seed)).random((n, d))
+    z = np.random.Generator(np.random.PCG64(2000 + t + seed)).standard_normal(n)
+    sq = np.sum(x * x, axis=1)
+    r2 = np.maximum(sq[:, None] + sq[None, :] - 2.0 * (x @ x.T), 0.0)  # l* = 1
+    k = np.exp(-0.5 * r2)
+    k[np.diag_indices(n)] = 1.0 + 0.01 + 1e-6
+    ys.append(5.0 + np.linalg.cholesky(k) @ z)
+    xs.append(x)
+  return np.stack(xs), np.stack(ys)[..., None]
 
 
 def init_raw(d):
@@ -138,58 +148,77 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------- reference arm ---
-def cpu_port_steps_per_sec(sample_tasks, steps, warmup, dtype_name="f64"):
-  """Times the CPU restatement of the reference step (torch-CPU op-by-op port
-  with autograd + Adam, all host threads) on a bounded sample of the workload
-  and scales to the full 256-task step."""
+def _host_cores():
+  try:
+    return len(os.sched_getaffinity(0))
+  except AttributeError:
+    return os.cpu_count() or 1
+
+
+def cpu_port_trainer(tasks, dtype_name="f64", batched=True):
+  """The CPU restatement of the reference step (torch-CPU op-by-op port with
+  autograd + Adam, oracle/hyperbo_oracle_torch.py) on `tasks` of the workload's
+  256 tasks, with all host threads (torchrun exports OMP_NUM_THREADS=1 to its
+  workers: a launcher default, not a property of the baseline)."""
   import torch
   from oracle import hyperbo_oracle_torch as OT
-  # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1
-  # to its workers: a launcher default, not a property of the baseline)
-  try:
-    ncores = len(os.sched_getaffinity(0))
-  except AttributeError:
-    ncores = os.cpu_count() or 1
+  ncores = _host_cores()
   if torch.get_num_threads() < ncores:
     torch.set_num_threads(ncores)
-  x, y = synthetic_batch(sample_tasks, N_PTS, DIM)
+  x, y = synthetic_batch(T_TASKS, N_PTS, DIM, tasks=tasks)
   model = {"constant": 5.1, "lengthscale": [0.0] * DIM, "signal_variance": 0.0,
            "noise_variance": -4.0}
   dt = torch.float64 if dtype_name == "f64" else torch.float32
-  tr = OT.AdamTrainer("constant", "squared_exponential", model, x, y, lr=LR,
-                      dtype=dt, batched=True)
+  return OT.AdamTrainer("constant", "squared_exponential", model, x, y, lr=LR,
+                        dtype=dt, batched=batched), torch.get_num_threads()
+
+
+def time_steps(tr, steps, warmup):
   for _ in range(warmup):
     tr.step()
   t0 = time.perf_counter()
+  loss = None
   for _ in range(steps):
-    tr.step()
-  dt_s = (time.perf_counter() - t0) / steps
-  full_step_s = dt_s * (T_TASKS / sample_tasks)
-  return 1.0 / full_step_s, dt_s, torch.get_num_threads()
+    loss = tr.step()
+  return (time.perf_counter() - t0) / steps, loss
 
 
 def run_reference(args):
+  """The reference's own CPU path for the SAME config, steps and warm-up: all
+  256 tasks per step (nothing sampled, nothing scaled).  JAX is not installable
+  in this image, so the arm is the op-by-op torch-CPU port of the reference step
+  (`kind: "port"`), task-batched (generous to the baseline: the reference loops
+  over tasks in Python, objectives.py:181); the task-looped variant is timed
+  next to it on one step."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  sample = 32
-  steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-  v, dt_s, cores = cpu_port_steps_per_sec(sample, steps, warmup)
+  tr, cores = cpu_port_trainer(range(T_TASKS), "f64", batched=True)
+  dt_s, loss = time_steps(tr, args.steps, args.warmup)
+  v = 1.0 / dt_s
+  looped = None
+  if not args.no_looped:
+    trl, _ = cpu_port_trainer(range(T_TASKS), "f64", batched=False)
+    dl, _ = time_steps(trl, 1, 0)
+    looped = {"value": 1.0 / dl, "unit": "steps/s", "steps": 1,
+              "what": "same step with the reference's Python loop over tasks "
+                      "(objectives.py:181) instead of one batched program"}
   line = {
       "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s",
-      "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
       "config": {"workload": "configs[1]: 256 tasks x n=512 x d=8 SE-ARD + "
                              "constant mean, fp64 NLL+grad+Adam step",
-                 "tasks": T_TASKS, "n": N_PTS, "d": DIM},
+                 "tasks": T_TASKS, "n": N_PTS, "d": DIM, "lr": LR},
+      "final_loss": loss,
       "cpu_baseline": {
           "value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-          "sample": f"{sample} of {T_TASKS} tasks per timed step "
-                    f"({dt_s:.3f} s each), scaled x{T_TASKS // sample}; "
-                    "torch-CPU op-by-op port of the reference step (JAX is "
-                    "not installable in this image), task-batched, all host "
-                    "threads"},
+          "sample": f"all {T_TASKS} tasks per step, {args.steps} timed steps after "
+                    f"{args.warmup} warm-up ({dt_s:.3f} s each); torch-CPU op-by-op "
+                    "port of the reference step (JAX is not installable in this "
+                    "image), task-batched, all host threads",
+          "task_looped": looped},
       "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0,
               "d2h_bytes_per_step": 0},
   }
@@ -210,81 +239,164 @@ def run_ours(args):
   torch.cuda.set_device(local)
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-  f32 = args.dtype == "f32"
-  tdt = torch.float32 if f32 else torch.float64
-  esz = 4 if f32 else 8
-  eng = Engine.get(local, dtype=tdt)
-  dev = eng.device
-
   T, n, d = T_TASKS, N_PTS, DIM
-  x_all, y_all = synthetic_batch(T, n, d)
   mine = shard_tasks(list(range(T)), rank, world)  # strong scaling
   Tl = len(mine)
-  x_host = torch.from_numpy(np.ascontiguousarray(x_all[mine].reshape(Tl * n, d))).to(tdt).pin_memory()
-  y_host = torch.from_numpy(np.ascontiguousarray(y_all[mine].reshape(Tl * n))).to(tdt).pin_memory()
-  ds = PackedDataset(mine, x_host.to(dev), y_host.to(dev),
-                     [n * t for t in range(Tl + 1)])
+  x_np, y_np = synthetic_batch(T, n, d, tasks=mine)
   mask = 0b110 | (((1 << d) - 1) << 3)
+  NWIN = max(1, args.windows)
 
-  def make_trainer():
-    return AdamTrainer(eng, 0, 1, init_raw(d), mask, d, LR, allreduce=world > 1)
-
-  def barrier():
+  def barrier(dev):
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize(dev)
 
-  def timed(trainer, from_host, steps, graph=True):
-    """K steps bracketed by barrier+sync, device-timed with CUDA events.  The
-    launch sequence of a step is replayed from a CUDA graph (single GPU)."""
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(steps):
-      # one read-back of the loss per step (the isfinite host check of
-      # gp.py:135-138), pipelined one step behind the enqueue
-      prev = trainer.step_pipelined(ds, x_host if from_host else None,
-                                    y_host if from_host else None,
-                                    use_graph=graph)
-      if prev is not None and not math.isfinite(prev):
-        raise FloatingPointError("non-finite loss in bench")
-    last = trainer.flush()
-    if not math.isfinite(last):
-      raise FloatingPointError("non-finite loss in bench")
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return float(ms) / steps, last
+  def measure(dtype_name, with_sections):
+    """-> dict with the device-resident and the host-buffer (e2e) timings of
+    the step for one engine precision."""
+    f32 = dtype_name == "f32"
+    tdt = torch.float32 if f32 else torch.float64
+    eng = Engine.get(local, dtype=tdt)
+    dev = eng.device
+    x_host = torch.from_numpy(np.ascontiguousarray(x_np.reshape(Tl * n, d))).to(tdt).pin_memory()
+    y_host = torch.from_numpy(np.ascontiguousarray(y_np.reshape(Tl * n))).to(tdt).pin_memory()
+    ds = PackedDataset(mine, x_host.to(dev), y_host.to(dev),
+                       [n * t for t in range(Tl + 1)])
 
-  # ---- device-resident run: `value`
-  tr = make_trainer()
-  l0 = eng.launch_count()
-  tr.step(ds)
-  launches_per_step = eng.launch_count() - l0
-  tr.loss()
-  for _ in range(max(args.warmup - 1, 2)):
-    tr.step(ds, use_graph=True)
+    def make_trainer():
+      return AdamTrainer(eng, 0, 1, init_raw(d), mask, d, LR, allreduce=world > 1)
+
+    def timed(trainer, from_host, steps, graph=True):
+      """K steps bracketed by barrier+sync, device-timed with CUDA events; max
+      over ranks.  One loss read-back per step (the isfinite host check of
+      gp.py:135-138), pipelined one step behind the enqueue."""
+      e0 = torch.cuda.Event(enable_timing=True)
+      e1 = torch.cuda.Event(enable_timing=True)
+      barrier(dev)
+      e0.record()
+      for _ in range(steps):
+        prev = trainer.step_pipelined(ds, x_host if from_host else None,
+                                      y_host if from_host else None,
+                                      use_graph=graph)
+        if prev is not None and not math.isfinite(prev):
+          raise FloatingPointError("non-finite loss in bench")
+      last = trainer.flush()
+      if not math.isfinite(last):
+        raise FloatingPointError("non-finite loss in bench")
+      e1.record()
+      barrier(dev)
+      ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+      if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+      return float(ms) / steps, last
+
+    def windows(trainer, from_host):
+      """NWIN windows of exactly K steps; the median window is the result."""
+      w = [timed(trainer, from_host, args.steps) for _ in range(NWIN)]
+      ms = sorted(v[0] for v in w)
+      return ms[len(ms) // 2], ms, w[-1][1]
+
+    tr = make_trainer()
+    l0 = eng.launch_count()
+    tr.step(ds)
+    launches_per_step = eng.launch_count() - l0
     tr.loss()
+    for _ in range(max(args.warmup - 1, 2)):
+      tr.step(ds, use_graph=True)
+      tr.loss()
+    res = {"eng": eng, "launches_per_step": launches_per_step, "esz": 4 if f32 else 8}
+    res["ms"], res["ms_windows"], res["loss"] = windows(tr, False)
+    if with_sections:
+      # the same K steps once more, eagerly, with the library's per-kernel CUDA
+      # events (events cannot be queried inside a graph): roofline numerators
+      eng.h.profile_enable(True)
+      res["ms_eager"], _ = timed(tr, False, args.steps, graph=False)
+      res["prof_ms"], res["prof_cnt"] = eng.h.profile_read()
+      eng.h.profile_enable(False)
+    # end to end through the public trainer with HOST buffers
+    tr2 = make_trainer()
+    for _ in range(3):
+      tr2.step_from_host(ds, x_host, y_host, use_graph=True)
+      tr2.loss()
+    res["ms_e2e"], res["ms_e2e_windows"], _ = windows(tr2, True)
+    res["h2d"] = int((x_host.numel() + y_host.numel()) * res["esz"])
+    res["ds"], res["x_host"], res["y_host"] = ds, x_host, y_host
+    return res
+
+  main_dt = args.dtype
   sampler = ClockSampler(local)
   sampler.start()
-  ms_step, loss = timed(tr, False, args.steps)
-  # same K steps once more, eagerly, with the library's per-kernel CUDA events
-  # (events cannot be queried inside a graph): roofline numerators
-  eng.h.profile_enable(True)
-  ms_step_eager, _ = timed(tr, False, args.steps, graph=False)
-  prof_ms, prof_cnt = eng.h.profile_read()
-  eng.h.profile_enable(False)
+  R = measure(main_dt, True)
   clocks = sampler.stop()
+  eng = R["eng"]
+  dev = eng.device
+  f32 = main_dt == "f32"
+  # the other precision, same steps (one line for the driver: configs[1] AND [2])
+  other = None
+  if not args.single_dtype:
+    other_dt = "f64" if f32 else "f32"
+    O = measure(other_dt, False)
+    other = {"dtype": other_dt, "value": 1e3 / O["ms"], "unit": "steps/s",
+             "ms_per_step": O["ms"], "ms_per_step_windows": O["ms_windows"],
+             "e2e_value": 1e3 / O["ms_e2e"], "final_loss": O["loss"],
+             "workload": "configs[2] (fp32 engine, same shapes)" if other_dt == "f32"
+                         else "configs[1] (fp64 engine, same shapes)"}
 
-  # ---- end-to-end run through the public trainer with HOST buffers
-  tr2 = make_trainer()
-  for _ in range(3):
-    tr2.step_from_host(ds, x_host, y_host, use_graph=True)
-    tr2.loss()
-  ms_e2e, _ = timed(tr2, True, args.steps)
+  # ---- e2e through the reference's entry point: GP(...).train() (gp.py:454-485)
+  e2e_train = None
+  if world == 1 and not args.no_train_e2e:
+    from hyperbo_b200.basics import definitions as defs
+    from hyperbo_b200.gp_utils import gp as gpm, kernel, mean, objectives, utils
+    from hyperbo_b200 import engine as engmod
+    engmod.set_default_dtype(torch.float32 if f32 else torch.float64)
+    dataset = {t: defs.SubDataset(x_np[i], y_np[i]) for i, t in enumerate(mine)}
+    K = args.steps
+
+    def train_once(steps):
+      params = defs.GPParams(
+          model={"constant": 5.1, "lengthscale": np.zeros(d), "signal_variance": 0.0,
+                 "noise_variance": -4.0},
+          config={"method": "adam", "learning_rate": LR, "max_training_step": steps,
+                  "batch_size": n + 1, "objective": objectives.nll})
+      model = gpm.GP(dataset, mean.constant, kernel.squared_exponential, params,
+                     utils.DEFAULT_WARP_FUNC)
+      torch.cuda.synchronize(dev)
+      t0 = time.perf_counter()
+      model.train(key=0)
+      torch.cuda.synchronize(dev)
+      return time.perf_counter() - t0
+
+    train_once(3)  # warm-up: workspace, plan, graph
+    wall = sorted(train_once(K) for _ in range(3))[1]
+    e2e_train = {"value": K / wall, "unit": "steps/s", "steps": K, "wall_s": wall,
+                 "path": "GP(dataset, mean.constant, kernel.squared_exponential, "
+                         "params).train(): host numpy dataset in, packing + upload "
+                         "+ K Adam steps + per-step loss read-back + the final "
+                         "acceptance evaluation, wall clock (median of 3)"}
+
+  # ---- factorise-only timings: the second half of BASELINE's metric
+  def chol_block(tag, T_, n_, d_, kid, reps):
+    rng = np.random.default_rng(11)
+    xs = torch.as_tensor(rng.random((T_ * n_, d_)), device=dev, dtype=eng.dtype)
+    ys = torch.as_tensor(5.0 + rng.standard_normal(T_ * n_), device=dev, dtype=eng.dtype)
+    dsc = PackedDataset(list(range(T_)), xs, ys, [n_ * t for t in range(T_ + 1)])
+    raw = init_raw(d_)
+    msk = 0b110 | (((1 << d_) - 1) << 3)
+    for _ in range(2):
+      eng.factorize(kid, 1, dsc, raw, msk, want_chol=False, want_alpha=False)
+    torch.cuda.synchronize(dev)
+    best = []
+    for _ in range(reps):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      eng.factorize(kid, 1, dsc, raw, msk, want_chol=False, want_alpha=False)
+      b.record()
+      torch.cuda.synchronize(dev)
+      best.append(a.elapsed_time(b))
+    ms = sorted(best)[len(best) // 2]
+    fl = T_ * n_**3 / 3.0
+    return {"config": tag, "tasks": T_, "n": n_, "d": d_, "ms": ms,
+            "flops_n3_over_3": fl, "achieved": fl / ms / 1e9, "unit": "TFLOP/s"}
 
   if rank != 0:
     if world > 1:
@@ -293,6 +405,7 @@ def run_ours(args):
 
   # ---- roofline denominators: measured tensor peak of the engine's precision:
   # cuBLAS DGEMM for fp64; cuBLAS TF32 GEMM / 3 for the fp32 engine (3xTF32)
+  tdt = eng.dtype
   if f32:
     torch.backends.cuda.matmul.allow_tf32 = True
   a = torch.randn(8192, 8192, device=dev, dtype=tdt)
@@ -308,96 +421,113 @@ def run_ours(args):
     s1.record()
     torch.cuda.synchronize(dev)
     best = min(best, s0.elapsed_time(s1))
-  dgemm_tf = 2 * 8192**3 / best / 1e9
+  peak_tf = 2 * 8192**3 / best / 1e9
   if f32:
-    dgemm_tf /= 3.0
+    peak_tf /= 3.0
   del a, b
+  peak_source = ("in-run cuBLAS TF32 GEMM 8192^3 best of 5, divided by 3 (the fp32 "
+                 "engine spends 3 TF32 MMAs per product)" if f32 else
+                 "in-run cuBLAS DGEMM 8192^3 best of 5 (fp64 tensor pipe; "
+                 "MEASURED_PEAKS.json holds no fp64 figure)")
+
+  cholesky = None
+  if world == 1 and not args.no_cholesky:
+    cholesky = [chol_block("configs[1]/[2]: 256 x 512 x 8 SE", T, n, d, 0, 5),
+                chol_block("configs[4]: 32 x 4096 x 16 Matern-5/2", 32, 4096, 16, 2, 3)]
+    for c in cholesky:
+      c["peak"] = peak_tf
+      c["frac"] = c["achieved"] / peak_tf
 
   fl = algorithmic_flops(Tl, n, d)
+  prof_ms, prof_cnt = R["prof_ms"], R["prof_cnt"]
+  ms_step = R["ms"]
+  # DRAM bytes of the dominant kernel from the committed ncu capture, valid for
+  # the task count it was taken at only (null otherwise)
   traffic = None
   tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
   if os.path.exists(tpath) and not f32:
     try:
-      traffic = json.load(open(tpath)).get("k_lauum_grad_dram_bytes_per_launch")
+      tj = json.load(open(tpath))
+      if tj.get("tasks_per_gpu") == Tl:
+        traffic = tj.get("k_fused_dram_bytes_per_launch")
     except Exception:
       traffic = None
 
-  def roof(flops, ms_total, count):
-    if not count:
-      return None
-    ms = ms_total / count
-    ach = flops / ms / 1e9
-    return {"bound": "tensor", "achieved": ach, "peak": dgemm_tf,
-            "unit": "TFLOP/s", "frac": ach / dgemm_tf, "ms_per_launch": ms}
-
-  roofline = roof(fl["lauum_grad"], prof_ms[2], prof_cnt[2]) or {}
-  roofline.update({
-      "kernel": "k_lauum_grad (largest single launch: K~^-1 = M'M tiles on the "
-                "fp64 tensor pipe + gradient contraction)",
-      "traffic": traffic,
-      "peak_source": ("in-run cuBLAS TF32 GEMM 8192^3 best of 5, divided by 3 "
-                      "(the fp32 engine spends 3 TF32 MMAs per product)" if f32
-                      else "in-run cuBLAS DGEMM 8192^3 best of 5 (fp64 tensor "
-                      "pipe; MEASURED_PEAKS.json holds no fp64 figure)"),
-      "flops_per_launch": fl["lauum_grad"],
-  })
-  roofline_factor = roof(fl["factor_launches"], prof_ms[0], prof_cnt[0]) or {}
-  roofline_factor.update({
-      "kernel": "k_step x (nblk+1) launches per step: kernel build + blocked "
-                "Cholesky + triangular inverse",
-      "flops_per_launch_group": fl["factor_launches"]})
+  # the dominant kernel IS the step: one persistent launch (k_fused) computes
+  # kernel tiles, Cholesky, inverse, alpha and the gradient contraction
+  ms_fused = prof_ms[2] / max(prof_cnt[2], 1)
+  ach = fl["step"] / ms_fused / 1e9
+  roofline = {
+      "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+      "frac": ach / peak_tf, "ms_per_launch": ms_fused, "traffic": traffic,
+      "kernel": "k_fused (persistent, dependency-driven: kernel-matrix tiles + "
+                "blocked Cholesky + triangular inverse + alpha + K~^-1 tiles with "
+                "the gradient contraction) -- the dominant kernel, ~98% of the step",
+      "peak_source": peak_source, "flops_per_launch": fl["step"],
+      "algorithmic_flops": "SURVEY 8(d): T (n^3 + 4 n^2 + n^2 (3d+8) + n^2 (2d+6))"}
   roofline_step = {
       "bound": "tensor", "achieved": fl["step"] / ms_step / 1e9,
-      "peak": dgemm_tf, "unit": "TFLOP/s",
-      "frac": fl["step"] / ms_step / 1e9 / dgemm_tf,
+      "peak": peak_tf, "unit": "TFLOP/s",
+      "frac": fl["step"] / ms_step / 1e9 / peak_tf,
       "flops_per_step": fl["step"]}
 
-  # ---- CPU baseline on this box's host cores (bounded sample)
+  # ---- CPU baseline on this box's host cores (bounded sample, rank 0, N=1)
   cpu = None
-  if not args.no_cpu_baseline:
-    sample = 32
-    v, dt_s, cores = cpu_port_steps_per_sec(sample, 3, 1, args.dtype)
-    cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-           "sample": f"{sample} of {T} tasks x 3 steps ({dt_s:.3f} s/step), "
-                     f"scaled x{T // sample}; torch-CPU port of the reference "
-                     f"step, {args.dtype}, task-batched"}
+  if not args.no_cpu_baseline and world == 1:
+    sample = 64
+    trc, cores = cpu_port_trainer(range(sample), main_dt, batched=True)
+    dt_s, _ = time_steps(trc, 3, 1)
+    cpu = {"value": 1.0 / (dt_s * T / sample), "unit": "steps/s", "cores": cores,
+           "kind": "port",
+           "sample": f"{sample} of {T} tasks x 3 steps after 1 warm-up "
+                     f"({dt_s:.3f} s/step), scaled x{T // sample} (the full-size "
+                     f"run is `--impl reference`); torch-CPU port of the reference "
+                     f"step, {main_dt}, task-batched"}
 
+  esz = R["esz"]
   line = {
       "metric": METRIC, "value": 1e3 / ms_step, "unit": "steps/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-      "ms_per_step": ms_step, "ms_per_step_eager_launches": ms_step_eager,
+      "ms_per_step": ms_step, "windows": NWIN,
+      "ms_per_step_windows": R["ms_windows"],
+      "ms_per_step_eager_launches": R["ms_eager"],
       "higher_is_better": True, "scaling": "strong",
-      "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+      "vs_baseline": None, "dtype": main_dt, "data": "synthetic",
       "config": {
           "workload": ("configs[2]" if f32 else "configs[1]") +
                       ": 256 tasks x n=512 x d=8 SE-ARD + constant mean, " +
                       ("fp32" if f32 else "fp64") +
-                      " NLL+grad+Adam step (tasks sharded t%N over "
-                      "N GPUs, one all-reduce of P+2 scalars per step)",
+                      " NLL+grad+Adam step (tasks sharded t%N over N GPUs, one "
+                      "peer-memory all-reduce of P+2 scalars fused with Adam per step)",
           "tasks": T, "n": n, "d": d, "tasks_per_gpu": Tl, "lr": LR,
-          "l2_policy": "no explicit flush: each step streams its packed L and "
-                       "L^-1 tiles (%.0f MB per GPU) through the 126 MB L2, so "
-                       "no step starts with its working set resident"
+          "inputs": "SURVEY 8(d): one draw per task from the ground-truth GP",
+          "timing": f"median of {NWIN} windows of {args.steps} steps each",
+          "l2_policy": "no explicit flush: each step streams its packed L, L^-1 "
+                       "and W tiles (%.0f MB per GPU) through the 126 MB L2, so no "
+                       "step starts with its working set resident"
                        % (3 * Tl * 36 * 4096 * esz / 1e6)},
-      "final_loss": loss,
+      "final_loss": R["loss"],
       "clocks": clocks,
-      "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
-              "h2d_bytes_per_step": int((x_host.numel() + y_host.numel()) * esz),
-              "d2h_bytes_per_step": esz,
+      "e2e": {"value": 1e3 / R["ms_e2e"], "unit": "steps/s",
+              "ms_per_step": R["ms_e2e"],
+              "ms_per_step_windows": R["ms_e2e_windows"],
+              "h2d_bytes_per_step": R["h2d"], "d2h_bytes_per_step": esz,
               "path": "gp.AdamTrainer.step_pipelined(ds, x_host, y_host): every "
                       "step uploads its batch from pinned host memory on a copy "
                       "stream into one of two device buffers (overlapping the "
                       "previous step's kernels) and reads its loss back"},
-      "gpu_launches": int(launches_per_step * args.steps),
-      "gpu_launches_per_step": int(launches_per_step),
+      "e2e_train": e2e_train,
+      "gpu_launches": int(R["launches_per_step"] * args.steps * NWIN),
+      "gpu_launches_per_step": int(R["launches_per_step"]),
       "roofline": roofline,
-      "roofline_factor_launches": roofline_factor,
       "roofline_step": roofline_step,
+      "cholesky": cholesky,
       "section_ms_per_step": {
-          "factor": prof_ms[0] / max(prof_cnt[0], 1),
-          "alpha": prof_ms[1] / max(prof_cnt[1], 1),
-          "lauum_grad": prof_ms[2] / max(prof_cnt[2], 1),
-          "reduce": 2 * prof_ms[3] / max(prof_cnt[3], 1)},
+          "prep": prof_ms[0] / max(prof_cnt[0], 1),
+          "k_fused": ms_fused,
+          "task_final": prof_ms[1] / max(prof_cnt[1], 1),
+          "reduce": prof_ms[3] / max(prof_cnt[3], 1)},
+      "other_precision": other,
       "cpu_baseline": cpu,
   }
   print(json.dumps(line), flush=True)
@@ -412,6 +542,14 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--windows", type=int, default=5,
+                  help="timed windows of --steps steps each (median reported)")
+  ap.add_argument("--single-dtype", action="store_true",
+                  help="skip the measurement of the other engine precision")
+  ap.add_argument("--no-train-e2e", action="store_true")
+  ap.add_argument("--no-cholesky", action="store_true")
+  ap.add_argument("--no-looped", action="store_true",
+                  help="reference arm: skip the task-looped variant")
   ap.add_argument("--tasks", type=int, default=None,
                   help="experiments only: total task count instead of 256")
   ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
