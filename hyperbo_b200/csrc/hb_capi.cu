@@ -70,6 +70,7 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   if (const char* e = getenv("HB_FUSED_GRID")) h->fused_grid = atoi(e);
   if (const char* e = getenv("HB_FUSED_SKEW")) h->fused_skew = atof(e);
   if (const char* e = getenv("HB_FUSED_GROUPS")) h->fused_groups = atoi(e);
+  if (const char* e = getenv("HB_FUSED_FASTPATH")) h->fused_fastpath = atoi(e) ? 1 : 0;
   if (const char* e = getenv("HB_FUSED_VT_DIAG")) h->fused_vt_diag = atof(e);
   {
     cudaDeviceProp prop;
@@ -118,6 +119,19 @@ const char* hb_last_error(hb_handle_t h) { return h ? h->err.c_str() : "null han
 int64_t hb_launch_count(hb_handle_t h) { return h ? h->launches : 0; }
 int64_t hb_workspace_bytes(hb_handle_t h) { return h ? (int64_t)total_ws(h) : 0; }
 int64_t hb_generation(hb_handle_t h) { return h ? (int64_t)h->generation : -1; }
+// debug: copy an internal workspace buffer to the host (tests / triage only)
+int64_t hb_debug_read(hb_handle_t h, int which, void* host_out, int64_t max_bytes) {
+  if (!h) return -1;
+  hb::host::Buf* bufs[] = {&h->Lt, &h->Mt, &h->Wt, &h->z, &h->alpha, &h->apart,
+                           &h->gpart, &h->gtask, &h->logdet, &h->nll_task, &h->sync};
+  if (which < 0 || which >= (int)(sizeof(bufs) / sizeof(bufs[0]))) return -1;
+  cudaDeviceSynchronize();
+  const int64_t nb = std::min<int64_t>(max_bytes, (int64_t)bufs[which]->cap);
+  if (host_out && nb > 0 &&
+      cudaMemcpy(host_out, bufs[which]->p, nb, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return (int64_t)bufs[which]->cap;
+}
 int hb_debug_fused_timeout(hb_handle_t h) {
   if (!h) return -1;
   return h->dtype == HB_F64 ? hb::f64::fused_timeout_impl() : hb::f32::fused_timeout_impl();

@@ -61,6 +61,7 @@ struct hb_handle_s {
   int fused = 1;               // HB_FUSED env: 0 = the launch-per-column path
   int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel
   double fused_skew = 0.0;     // HB_FUSED_SKEW env: task skew of the item order
+  int fused_fastpath = 1;      // HB_FUSED_FASTPATH env: 0 = acquire-poll every dependency
   int fused_groups = 0;        // HB_FUSED_GROUPS env: work queues (0 = automatic)
   double fused_vt_diag = 0.4;  // HB_FUSED_VT_DIAG env: queue position of DIAG(j+1)
   int fused_per_sm[2][hb::MAX_DIM + 1] = {};  // cached occupancy per (mapping, d)

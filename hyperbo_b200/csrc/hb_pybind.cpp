@@ -122,6 +122,10 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("generation", [](Handle& s) { return hb_generation(s.h); })
       .def("debug_fused_timeout", [](Handle& s) { return hb_debug_fused_timeout(s.h); })
+      .def("debug_read",
+           [](Handle& s, int which, ptr_t host_out, int64_t max_bytes) {
+             return hb_debug_read(s.h, which, P(host_out), max_bytes);
+           })
       .def("comm_export",
            [](Handle& s) {
              char buf[HB_IPC_HANDLE_BYTES];

@@ -86,6 +86,11 @@ int64_t hb_generation(hb_handle_t h);
 /* Debug: synchronises the device and returns 1 if a work item of the persistent
  * kernel ever gave up waiting for a dependency (a scheduling bug), else 0. */
 int hb_debug_fused_timeout(hb_handle_t h);
+/* Debug: synchronises and copies an internal workspace buffer to the host;
+ * which: 0 L tiles, 1 M tiles, 2 W tiles, 3 z, 4 alpha, 5 apart|rpart, 6 gpart,
+ * 7 gtask, 8 logdet, 9 nll_task, 10 sync words.  Returns the buffer's capacity
+ * in bytes (or -1). */
+int64_t hb_debug_read(hb_handle_t h, int which, void* host_out, int64_t max_bytes);
 /* Per-kernel timing for bench.py's roofline: when enabled, CUDA events are
  * recorded on the caller's stream around each section of
  * hb_nll_grad_batched / hb_factorize_batched:

@@ -1,0 +1,37 @@
+"""Determinism under re-use of the engine workspace: the persistent kernel's
+items communicate through global-memory flags, and every workspace buffer still
+holds the previous call's (plausible, wrong) data when a call starts.  A missing
+dependency or a stale read therefore shows up as sums that depend on what ran
+before.  The arithmetic is deterministic, so a batch must give BIT-IDENTICAL
+sums whatever preceded it -- in the few-task regime (items wait on flags) and
+the many-task regime (fast paths) alike."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T,n,trials", [(8, 512, 40), (32, 512, 40), (48, 300, 40),
+                                        (160, 200, 20)])
+def test_sums_do_not_depend_on_the_previous_call(T, n, trials):
+  from hyperbo_b200.engine import Engine
+  eng = Engine.get()
+  d = 8
+  raw = np.concatenate([[5.1, 0.0, -4.0], np.linspace(-0.3, 0.4, d)])
+  mask = 0b110 | (((1 << d) - 1) << 3)
+  rng = np.random.default_rng(T)
+  x = rng.random((2, T, n, d))
+  y = 5 + rng.standard_normal((2, T, n, 1))
+  pk_a = eng.pack([(t, x[0, t], y[0, t]) for t in range(T)])
+  pk_b = eng.pack([(t, x[1, t], y[1, t]) for t in range(T)])
+  ref = eng.nll_grad(0, 1, pk_a, raw, mask).cpu().numpy()
+  assert np.all(np.isfinite(ref))
+  for trial in range(trials):
+    if trial % 3 == 0:
+      eng.nll_grad(2, 1, pk_a, raw * 0.5, mask)          # other kernel / params
+    elif trial % 3 == 1:
+      eng.nll_grad(0, 1, pk_b, raw * 0.9, mask)          # other data
+    else:
+      eng.factorize(1, 1, pk_b, raw * 1.3, mask, want_chol=False)  # other entry
+    got = eng.nll_grad(0, 1, pk_a, raw, mask).cpu().numpy()
+    assert np.array_equal(got, ref), (trial, got - ref)
