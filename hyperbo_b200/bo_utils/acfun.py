@@ -123,6 +123,16 @@ ucb3 = acfun_wrapper(acfun_sub=ucb_sub, acfun_callback_default=lambda a, b: 3.)
 ucb2 = acfun_wrapper(acfun_sub=ucb_sub, acfun_callback_default=lambda a, b: 2.)
 ucb = ucb3
 
+# what the device-resident BO loop (bayesopt.simulated_bayesopt fast path) needs
+# to know about an acquisition whose callback is the default one:
+# (acq_id, parameter, parameter is an offset on max(y_observed))
+expected_improvement.hb_device = (1, 0.0, True)
+probability_of_improvement.hb_device = (2, 0.1, True)
+pi3.hb_device = (2, 0.05, True)
+ucb4.hb_device = (3, 4.0, False)
+ucb3.hb_device = (3, 3.0, False)
+ucb2.hb_device = (3, 2.0, False)
+
 random_search.__name__ = "random_search"
 rand = random_search
 

@@ -29,6 +29,12 @@ using namespace hb::host;
                        const void*, void*, void*);
 namespace hb {
 #define HB_COMM_PROTOTYPES                                                      \
+  int bo_init_impl(hb_handle_t, int, int, int64_t, int64_t, int, const void*,   \
+                   const void*, const void*, uint64_t, void*, void*);           \
+  int bo_step_impl(hb_handle_t, int, int, int64_t, int64_t, int, void*, void*,  \
+                   const void*, uint64_t, void*, int64_t, const void*,          \
+                   const void*, double, double, int, double, int, int32_t*,     \
+                   void*);                                                      \
   int fused_timeout_impl();                                                     \
   int allreduce_impl(hb_handle_t, void*, int, void*);                           \
   int allreduce_adam_impl(hb_handle_t, int, void*, void*, void*, void*, void*,  \
@@ -299,6 +305,30 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
   HB_DISPATCH(predict_impl, h, kernel_id, mean_id, n, d, X, cache, raw,
               warp_mask, nq, Xq, noise_add_flag, var_scale, acq_id, acq_param,
               mu_out, var_out, acq_out, stream);
+}
+
+int64_t hb_bo_cache_bytes(hb_handle_t h, int64_t n_cap) {
+  if (n_cap < 1) return -1;
+  const int64_t es = (h && h->dtype == HB_F32) ? 4 : 8;
+  const int64_t cb = (n_cap + TB - 1) / TB;
+  return (cb * (cb + 1) / 2 * TILE_ELEMS + cb * TB + 64) * es + 256;
+}
+
+int hb_bo_init(hb_handle_t h, int kernel_id, int mean_id, int64_t n0, int64_t n_cap,
+               int d, const void* X, const void* y, const void* raw,
+               uint64_t warp_mask, void* cache, void* stream) {
+  HB_DISPATCH(bo_init_impl, h, kernel_id, mean_id, n0, n_cap, d, X, y, raw, warp_mask,
+              cache, stream);
+}
+
+int hb_bo_step(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int64_t n_cap,
+               int d, void* X, void* y, const void* raw, uint64_t warp_mask,
+               void* cache, int64_t nq, const void* Xq, const void* yq,
+               double noise_add_flag, double var_scale, int acq_id, double acq_param,
+               int target_is_ymax, int32_t* sel_out, void* stream) {
+  HB_DISPATCH(bo_step_impl, h, kernel_id, mean_id, n, n_cap, d, X, y, raw, warp_mask,
+              cache, nq, Xq, yq, noise_add_flag, var_scale, acq_id, acq_param,
+              target_is_ymax, sel_out, stream);
 }
 
 int hb_acquisition(hb_handle_t h, int acq_id, double acq_param, int64_t nq,

@@ -57,6 +57,7 @@ struct hb_handle_s {
   hb::host::Buf theta, Lt, Mt, Wt, zz, z, alpha, logdet, asum, nll_task, gpart, gtask, info, bad,
       sums, kst, mupart, vpart, pcache, stamps, pre, sync, apart;
   bool attr_set = false;
+  bool bo_attr_set = false;
   int sm_count = 0;
   int fused = 1;               // HB_FUSED env: 0 = the launch-per-column path
   int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel

@@ -122,6 +122,25 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("generation", [](Handle& s) { return hb_generation(s.h); })
       .def("debug_fused_timeout", [](Handle& s) { return hb_debug_fused_timeout(s.h); })
+      .def("bo_cache_bytes", [](Handle& s, int64_t n_cap) { return hb_bo_cache_bytes(s.h, n_cap); })
+      .def("bo_init",
+           [](Handle& s, int kernel_id, int mean_id, int64_t n0, int64_t n_cap, int d,
+              ptr_t X, ptr_t y, ptr_t raw, uint64_t mask, ptr_t cache, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_bo_init(s.h, kernel_id, mean_id, n0, n_cap, d, P(X), P(y), P(raw),
+                                mask, P(cache), P(stream)), "hb_bo_init");
+           })
+      .def("bo_step",
+           [](Handle& s, int kernel_id, int mean_id, int64_t n, int64_t n_cap, int d,
+              ptr_t X, ptr_t y, ptr_t raw, uint64_t mask, ptr_t cache, int64_t nq,
+              ptr_t Xq, ptr_t yq, double noise_flag, double var_scale, int acq_id,
+              double acq_param, int target_is_ymax, ptr_t sel, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_bo_step(s.h, kernel_id, mean_id, n, n_cap, d, P(X), P(y), P(raw),
+                                mask, P(cache), nq, P(Xq), P(yq), noise_flag, var_scale,
+                                acq_id, acq_param, target_is_ymax, (int32_t*)P(sel),
+                                P(stream)), "hb_bo_step");
+           })
       .def("debug_read",
            [](Handle& s, int which, ptr_t host_out, int64_t max_bytes) {
              return hb_debug_read(s.h, which, P(host_out), max_bytes);

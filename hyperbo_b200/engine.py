@@ -343,3 +343,73 @@ class Engine:
     self.h.acquisition(acq_id, float(param), mu.shape[0], mu.data_ptr(),
                        var.data_ptr(), out.data_ptr(), self._stream())
     return out.reshape(-1, 1)
+
+
+class BoSession:
+  """Device-resident simulated-BO state of one queried task (hb_bo_init /
+  hb_bo_step): observations, candidates and the packed inverse factor stay on
+  the GPU; one `step` = acquisition over all candidates + arg-max + append of
+  the chosen (x, y) + O(n^2) rank-1 update, with no host synchronisation."""
+
+  def __init__(self, eng: Engine, kernel_id: int, mean_id: int, x0, y0, raw,
+               mask: int, capacity: int, d: Optional[int] = None):
+    self.eng, self.kid, self.mid, self.mask = eng, kernel_id, mean_id, mask
+    x0 = eng.tensor(x0) if x0 is not None and len(x0) else None
+    self.n = 0 if x0 is None else int(x0.shape[0])
+    self.d = int(d if x0 is None else x0.shape[1])
+    eng._check_dim(self.d)
+    self.cap = int(capacity)
+    if self.cap < self.n + 1:
+      raise ValueError("capacity must exceed the number of initial observations")
+    self.x = torch.zeros((self.cap, self.d), device=eng.device, dtype=eng.dtype)
+    self.y = torch.zeros((self.cap,), device=eng.device, dtype=eng.dtype)
+    if self.n:
+      self.x[:self.n] = x0
+      self.y[:self.n] = eng.tensor(y0).reshape(-1)
+    self.raw = eng.tensor(raw)
+    self.cache = torch.empty((int(eng.h.bo_cache_bytes(self.cap)),),
+                             device=eng.device, dtype=torch.uint8)
+    self.sel = torch.full((self.cap,), -1, device=eng.device, dtype=torch.int32)
+    self.n0 = self.n
+    eng.h.bo_init(kernel_id, mean_id, self.n, self.cap, self.d, self.x.data_ptr(),
+                  self.y.data_ptr(), self.raw.data_ptr(), mask,
+                  self.cache.data_ptr(), eng._stream())
+
+  def step(self, xq: torch.Tensor, yq: torch.Tensor, acq_id: int, acq_param: float,
+           target_is_ymax: bool, noise_flag=1.0, var_scale=1.0):
+    """xq (nq, d), yq (nq,) device tensors of the engine's dtype."""
+    if self.n + 1 > self.cap:
+      raise ValueError("BoSession capacity exhausted")
+    self.eng.h.bo_step(self.kid, self.mid, self.n, self.cap, self.d,
+                       self.x.data_ptr(), self.y.data_ptr(), self.raw.data_ptr(),
+                       self.mask, self.cache.data_ptr(), int(xq.shape[0]),
+                       xq.data_ptr(), yq.data_ptr(), float(noise_flag),
+                       float(var_scale), int(acq_id), float(acq_param),
+                       int(bool(target_is_ymax)),
+                       self.sel[self.n - self.n0:].data_ptr(), self.eng._stream())
+    self.n += 1
+
+  def selected(self) -> torch.Tensor:
+    """Indices of the candidates chosen so far (one device->host read)."""
+    return self.sel[:self.n - self.n0].cpu()
+
+  def observations(self):
+    return self.x[:self.n], self.y[:self.n].reshape(-1, 1)
+
+  def predict(self, xq, noise_flag=0.0, var_scale=1.0):
+    """Posterior at xq from the session's (appended) factor -- for tests."""
+    eng = self.eng
+    xq = eng.tensor(xq)
+    # the growable layout keeps alpha at the capacity's offset: predict through a
+    # compact copy (M tiles of the current n, then alpha)
+    nblk = (self.n + 63) // 64
+    es = 8 if eng.dtype == torch.float64 else 4
+    cap_blk = (self.cap + 63) // 64
+    mt = nblk * (nblk + 1) // 2 * 4096 * es
+    al_off = cap_blk * (cap_blk + 1) // 2 * 4096 * es
+    compact = torch.empty((mt + nblk * 64 * es + 256,), device=eng.device,
+                          dtype=torch.uint8)
+    compact[:mt] = self.cache[:mt]
+    compact[mt:mt + nblk * 64 * es] = self.cache[al_off:al_off + nblk * 64 * es]
+    return eng.predict(self.kid, self.mid, self.x[:self.n], compact, self.raw,
+                       self.mask, xq, noise_flag=noise_flag, var_scale=var_scale)

@@ -746,6 +746,14 @@ class GP:
                             dtype=cov.dtype) * nv
     return mu, cov * scale
 
+  def engine_ids(self, d: int):
+    """(kernel_id, mean_id, raw, warp_mask) of this model for the C ABI."""
+    kid = _kernel.kernel_id_of(self.cov_func)
+    mid = _mean.mean_id_of(self.mean_func)
+    raw, mask, _ = params_utils.pack_raw(self.params.model, d, mid == 1,
+                                         self.warp_func)
+    return kid, mid, raw, mask
+
   def acquisition(self, queried_inputs, sub_dataset_key, acq_id, acq_param):
     """Fused predict + acfun_sub epilogue (acfun.py:84-88 + :96-142) with the
     GP.predict conventions full_cov=False, with_noise=True, unbiased=True."""

@@ -241,6 +241,35 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
 int hb_acquisition(hb_handle_t h, int acq_id, double acq_param, int64_t nq,
                    const void* mu, const void* var, void* out, void* stream);
 
+/* ---- 8(f) rank 1: device-resident simulated Bayesian optimisation -------- */
+/* bo_utils/bayesopt.py:137-193 per iteration: evaluate the acquisition on ALL
+ * candidates, take the arg-max, append the chosen (x, y) to the queried task
+ * (gp.py:446-452) and re-condition the GP.  The reference refactorises from
+ * scratch every iteration (gp.py:284: "one can potentially support rank-1
+ * updates"); hb_bo_step keeps observations, candidates and the factor on the
+ * device and appends one row to the packed L^{-1} tiles and alpha in O(n^2),
+ * with no host synchronisation inside the loop.
+ *   cache      : hb_bo_cache_bytes(n_cap) bytes, filled by hb_bo_init from the
+ *                first n0 observations (n0 = 0 allowed: prior prediction, EI/PI
+ *                target 0.0 as acfun.py:145-148);
+ *   X, y       : (n_cap, d) / (n_cap,) device buffers; rows < n are the
+ *                observations, hb_bo_step writes row n;
+ *   acquisition: acq_id as hb_predict; its parameter is acq_param (UCB beta), or
+ *                max(y_observed) + acq_param when target_is_ymax != 0 (EI: +0,
+ *                PI: + zeta), GP.predict's with_noise / N/(N-1) conventions via
+ *                noise_add_flag / var_scale;
+ *   sel_out    : device int32, receives the index of the chosen candidate.
+ * Call with n = n0, n0+1, ... (n + 1 <= n_cap). */
+int64_t hb_bo_cache_bytes(hb_handle_t h, int64_t n_cap);
+int hb_bo_init(hb_handle_t h, int kernel_id, int mean_id, int64_t n0, int64_t n_cap,
+               int d, const void* X, const void* y, const void* raw,
+               uint64_t warp_mask, void* cache, void* stream);
+int hb_bo_step(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int64_t n_cap,
+               int d, void* X, void* y, const void* raw, uint64_t warp_mask,
+               void* cache, int64_t nq, const void* Xq, const void* yq,
+               double noise_add_flag, double var_scale, int acq_id, double acq_param,
+               int target_is_ymax, int32_t* sel_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
