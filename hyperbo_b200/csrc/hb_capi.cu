@@ -29,6 +29,9 @@ using namespace hb::host;
                        const void*, void*, void*);
 namespace hb {
 #define HB_COMM_PROTOTYPES                                                      \
+  int subsample_impl(hb_handle_t, int, int, const void*, const void*,           \
+                     const void*, int64_t, const void*, const void*, void*,     \
+                     void*, uint64_t, const void*, int64_t, void*);             \
   int bo_init_impl(hb_handle_t, int, int, int64_t, int64_t, int, const void*,   \
                    const void*, const void*, uint64_t, void*, void*);           \
   int bo_step_impl(hb_handle_t, int, int, int64_t, int64_t, int, void*, void*,  \
@@ -305,6 +308,23 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
   HB_DISPATCH(predict_impl, h, kernel_id, mean_id, n, d, X, cache, raw,
               warp_mask, nq, Xq, noise_add_flag, var_scale, acq_id, acq_param,
               mu_out, var_out, acq_out, stream);
+}
+
+int hb_subsample(hb_handle_t h, int T, int d, const void* offs_src_dev,
+                 const void* offs_dst_dev, const void* task_ids_dev, int64_t max_rows,
+                 const void* Xs, const void* ys, void* Xd, void* yd, uint64_t seed,
+                 const void* step_scalars_dev, int64_t step, void* stream) {
+  HB_DISPATCH(subsample_impl, h, T, d, offs_src_dev, offs_dst_dev, task_ids_dev, max_rows,
+              Xs, ys, Xd, yd, seed, step_scalars_dev, step, stream);
+}
+
+// the permutation hb_subsample uses, for host-side checks (tests)
+uint32_t hb_subsample_perm(uint32_t i, uint32_t n, uint64_t seed, uint64_t step,
+                           int64_t task_id) {
+  const unsigned long long key = hb::hb_mix64(
+      hb::hb_mix64(seed ^ 0x5851f42d4c957f2dULL) +
+      hb::hb_mix64(step) * 0x2545f4914f6cdd1dULL + (unsigned long long)task_id);
+  return hb::hb_feistel_perm(i, n, key);
 }
 
 int64_t hb_bo_cache_bytes(hb_handle_t h, int64_t n_cap) {

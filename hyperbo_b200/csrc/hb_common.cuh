@@ -241,4 +241,32 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
+// counter-based generator of the device-side sub-sampling (hb_subsample)
+__host__ __device__ __forceinline__ unsigned long long hb_mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ unsigned hb_feistel_perm(unsigned i, unsigned n,
+                                                             unsigned long long key) {
+  unsigned hb = 1;  // half width in bits: 2^(2 hb) >= n
+  while ((1ull << (2 * hb)) < n) ++hb;
+  const unsigned hmask = (1u << hb) - 1u;
+  unsigned x = i;
+  do {
+    unsigned l = x >> hb, r = x & hmask;
+#pragma unroll
+    for (int rnd = 0; rnd < 6; ++rnd) {
+      const unsigned f = (unsigned)hb_mix64(key + ((unsigned long long)rnd << 56) + r) & hmask;
+      const unsigned nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (l << hb) | r;
+  } while (x >= n);  // cycle walking keeps the map a bijection of [0, n)
+  return x;
+}
+
+
 }  // namespace hb

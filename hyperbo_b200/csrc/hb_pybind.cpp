@@ -42,6 +42,8 @@ struct Handle {
 }  // namespace
 
 PYBIND11_MODULE(_C, m) {
+  m.def("subsample_perm", [](uint32_t i, uint32_t n, uint64_t seed, uint64_t step,
+                             int64_t task) { return hb_subsample_perm(i, n, seed, step, task); });
   m.doc() = "hyperbo_b200 C-ABI bindings";
   m.def("version", [] { return std::string(hb_version()); });
   m.attr("MAX_DIM") = HB_MAX_DIM;
@@ -122,6 +124,15 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("generation", [](Handle& s) { return hb_generation(s.h); })
       .def("debug_fused_timeout", [](Handle& s) { return hb_debug_fused_timeout(s.h); })
+      .def("subsample",
+           [](Handle& s, int T, int d, ptr_t offs_src, ptr_t offs_dst, ptr_t ids,
+              int64_t max_rows, ptr_t Xs, ptr_t ys, ptr_t Xd, ptr_t yd, uint64_t seed,
+              ptr_t scal, int64_t step, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_subsample(s.h, T, d, P(offs_src), P(offs_dst), P(ids), max_rows,
+                                  P(Xs), P(ys), P(Xd), P(yd), seed, P(scal), step,
+                                  P(stream)), "hb_subsample");
+           })
       .def("bo_cache_bytes", [](Handle& s, int64_t n_cap) { return hb_bo_cache_bytes(s.h, n_cap); })
       .def("bo_init",
            [](Handle& s, int kernel_id, int mean_id, int64_t n0, int64_t n_cap, int d,

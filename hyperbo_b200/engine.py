@@ -345,6 +345,46 @@ class Engine:
     return out.reshape(-1, 1)
 
 
+class DeviceSampler:
+  """Per-step sub-sampling on the device (hb_subsample; data_utils.py:72-100):
+  `dst` is a packed batch of FIXED shape -- task t keeps min(n_t, batch_size)
+  rows if n_t >= batch_size, else all n_t -- that `sample()` refills from the
+  full packed batch `src` with a uniform random subset per (seed, step, global
+  task id).  With `scal` (the trainer's scalars, [1] = step counter) the call
+  is CUDA-graph capturable: every replay draws a new sample."""
+
+  def __init__(self, eng: "Engine", src: PackedDataset, batch_size: int, seed: int,
+               task_ids: Optional[Sequence[int]] = None):
+    self.eng, self.src, self.seed = eng, src, int(seed) & ((1 << 63) - 1)
+    T = src.num_tasks
+    ns = [src.offs[t + 1] - src.offs[t] for t in range(T)]
+    nd = [batch_size if n >= batch_size else n for n in ns]
+    offs_dst = [0]
+    for n in nd:
+      offs_dst.append(offs_dst[-1] + n)
+    self.max_rows = max(nd) if nd else 0
+    dev = eng.device
+    self.offs_src_d = torch.tensor(src.offs, dtype=torch.int64, device=dev)
+    self.offs_dst_d = torch.tensor(offs_dst, dtype=torch.int64, device=dev)
+    ids = list(range(T)) if task_ids is None else [int(i) for i in task_ids]
+    self.ids_d = torch.tensor(ids, dtype=torch.int64, device=dev)
+    self.dst = PackedDataset(src.keys,
+                             torch.empty((offs_dst[-1], src.d), device=dev, dtype=eng.dtype),
+                             torch.empty((offs_dst[-1],), device=dev, dtype=eng.dtype),
+                             offs_dst)
+    self.dst.sampler = self
+
+  def sample(self, step: int = 0, scal: Optional[torch.Tensor] = None):
+    s, d_ = self.src, self.dst
+    self.eng.h.subsample(s.num_tasks, s.d, self.offs_src_d.data_ptr(),
+                         self.offs_dst_d.data_ptr(), self.ids_d.data_ptr(),
+                         self.max_rows, s.x.data_ptr(), s.y.data_ptr(),
+                         d_.x.data_ptr(), d_.y.data_ptr(), self.seed,
+                         scal.data_ptr() if scal is not None else 0, int(step),
+                         self.eng._stream())
+    return d_
+
+
 class BoSession:
   """Device-resident simulated-BO state of one queried task (hb_bo_init /
   hb_bo_step): observations, candidates and the packed inverse factor stay on

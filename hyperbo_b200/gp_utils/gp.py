@@ -97,6 +97,11 @@ class AdamTrainer:
       # all-reduce are the program's; sums = [value, gradient, 1]
       ds.sums(self.raw, self.mask, out=self.sums)
     else:
+      sampler = getattr(ds, "sampler", None)
+      if sampler is not None:
+        # per-step sub-sampling on the device, keyed by the step counter the
+        # Adam kernel maintains in scal[1] (data_utils.py:72-100)
+        sampler.sample(scal=self.scal)
       self.eng.nll_grad(self.kid, self.mid, ds, self.raw, self.mask,
                         sums_out=self.sums)
       if self.allreduce:
@@ -407,6 +412,17 @@ def infer_parameters(mean_func,
   dataset_iter = data_utils.sub_sample_dataset_iterator(key, dataset,
                                                         batch_size)
   static_ds = None if needs_subsample else pack(dataset)
+  if (needs_subsample and plain_nll and getattr(eng, "h", None) is not None and
+      os.environ.get("HB_DEVICE_SUBSAMPLE", "1") != "0"):
+    # sub-sample on the device into a fixed-shape packed batch: the step keeps
+    # its CUDA graph and no batch is re-packed on the host (the host iterator
+    # below remains for objective programs and the CPU test double)
+    items = obj._select(dataset, exclude_aligned=True)  # pylint: disable=protected-access
+    ids = shard_tasks(list(range(len(items))), rank, world)
+    src = eng.pack(shard_tasks(items, rank, world))
+    seed = (int(key.initial_seed()) if isinstance(key, torch.Generator) else int(key))
+    static_ds = _engine.DeviceSampler(eng, src, batch_size, seed, task_ids=ids).dst
+    needs_subsample = False
   any_x = next(iter(dataset.values())).x
   d = int(torch.as_tensor(any_x).shape[1])
   raw0, mask, scalar_ls = params_utils.pack_raw(params.model, d, mid == 1,

@@ -241,6 +241,25 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
 int hb_acquisition(hb_handle_t h, int acq_id, double acq_param, int64_t nq,
                    const void* mu, const void* var, void* out, void* stream);
 
+/* ---- a11: per-step sub-sampling on the device --------------------------- */
+/* data_utils.sub_sample_dataset_iterator (basics/data_utils.py:72-100): tasks
+ * with n >= batch_size are replaced, every step, by batch_size of their points
+ * drawn uniformly without replacement; others pass unchanged.  hb_subsample
+ * gathers such a sample of a packed source batch into a packed destination
+ * batch of FIXED shape (n'_t = offs_dst[t+1] - offs_dst[t] = min(n_t,
+ * batch_size) or n_t), keyed by (seed, step, task_ids[t]) with a counter-based
+ * generator, so the result does not depend on the task sharding.  The step is
+ * read from step_scalars_dev[1] (the step counter hb_adam_step maintains) when
+ * that pointer is given -- the call can then sit in the step's CUDA graph --
+ * else from `step`.  offs_* / task_ids: int64 DEVICE arrays (T+1 / T). */
+int hb_subsample(hb_handle_t h, int T, int d, const void* offs_src_dev,
+                 const void* offs_dst_dev, const void* task_ids_dev, int64_t max_rows,
+                 const void* Xs, const void* ys, void* Xd, void* yd, uint64_t seed,
+                 const void* step_scalars_dev_or_null, int64_t step, void* stream);
+/* The permutation hb_subsample applies: source row of destination row i. */
+uint32_t hb_subsample_perm(uint32_t i, uint32_t n, uint64_t seed, uint64_t step,
+                           int64_t task_id);
+
 /* ---- 8(f) rank 1: device-resident simulated Bayesian optimisation -------- */
 /* bo_utils/bayesopt.py:137-193 per iteration: evaluate the acquisition on ALL
  * candidates, take the arg-max, append the chosen (x, y) to the queried task
