@@ -29,6 +29,13 @@ using namespace hb::host;
                        const void*, void*, void*);
 namespace hb {
 #define HB_COMM_PROTOTYPES                                                      \
+  int nll_grad_multi_impl(hb_handle_t, int, int, int, int, const int64_t*, int, \
+                          const void*, const void*, const void*, uint64_t,      \
+                          void*, void*, void*);                                 \
+  int build_predictors_multi_impl(hb_handle_t, int, int, int, int64_t, int,     \
+                                  const void*, const void*, const void*,        \
+                                  uint64_t, void*, int64_t, void*, int32_t*,    \
+                                  void*);                                       \
   int subsample_impl(hb_handle_t, int, int, const void*, const void*,           \
                      const void*, int64_t, const void*, const void*, void*,     \
                      void*, uint64_t, const void*, int64_t, void*);             \
@@ -308,6 +315,23 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
   HB_DISPATCH(predict_impl, h, kernel_id, mean_id, n, d, X, cache, raw,
               warp_mask, nq, Xq, noise_add_flag, var_scale, acq_id, acq_param,
               mu_out, var_out, acq_out, stream);
+}
+
+int hb_nll_grad_multi(hb_handle_t h, int kernel_id, int mean_id, int S, int T,
+                      const int64_t* offs, int d, const void* X, const void* y,
+                      const void* raw_sets, uint64_t warp_mask, void* sums_out,
+                      void* nll_task_out, void* stream) {
+  HB_DISPATCH(nll_grad_multi_impl, h, kernel_id, mean_id, S, T, offs, d, X, y, raw_sets,
+              warp_mask, sums_out, nll_task_out, stream);
+}
+
+int hb_build_predictors_multi(hb_handle_t h, int kernel_id, int mean_id, int S, int64_t n,
+                              int d, const void* X, const void* y, const void* raw_sets,
+                              uint64_t warp_mask, void* caches,
+                              int64_t cache_stride_bytes, void* nll_out,
+                              int32_t* info_out, void* stream) {
+  HB_DISPATCH(build_predictors_multi_impl, h, kernel_id, mean_id, S, n, d, X, y, raw_sets,
+              warp_mask, caches, cache_stride_bytes, nll_out, info_out, stream);
 }
 
 int hb_subsample(hb_handle_t h, int T, int d, const void* offs_src_dev,

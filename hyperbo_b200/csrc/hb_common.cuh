@@ -34,6 +34,8 @@ struct TaskDesc {
   long long voff;      // offset into 64-padded per-task vectors (z, alpha)
   long long tile_off;  // first tile slot of this task in the packed buffers
   long long chol_off;  // element offset of this task's (n,n) row-major factor
+  int theta_idx;       // which hyper-parameter set (second batch axis; 0 if one)
+  int pad_;
 };
 
 __host__ __device__ __forceinline__ int tri_idx(int i, int j) {

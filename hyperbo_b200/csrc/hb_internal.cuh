@@ -25,7 +25,8 @@ struct Buf {
 
 struct Plan {
   std::vector<int64_t> offs;
-  int T = 0, d = 0;
+  int T = 0, d = 0;   // T = virtual tasks = S * (tasks of the batch)
+  int S = 1;          // hyper-parameter sets (second batch axis)
   std::vector<TaskDesc> tasks;
   TaskDesc* tasks_d = nullptr;
   size_t tasks_cap = 0;
@@ -125,13 +126,17 @@ inline size_t total_ws(hb_handle_t h) {
 }
 
 // find or build the plan for (T, offs, d); uploads descriptors when new
-inline int get_plan(hb_handle_t h, int T, const int64_t* offs, int d, cudaStream_t st,
-             Plan** out) {
+// S > 1: S hyper-parameter sets x the same Tb = T tasks: virtual task s * Tb + t
+// reads the data rows of task t and the parameter set s, and owns its own
+// workspace tiles
+inline int get_plan(hb_handle_t h, int Tb, const int64_t* offs, int d, cudaStream_t st,
+             Plan** out, int S = 1) {
   ++h->clock;
+  const int T = Tb * S;
   Plan* lru = &h->plans[0];
   for (auto& p : h->plans) {
-    if (p.uploaded && p.T == T && p.d == d && (int)p.offs.size() == T + 1 &&
-        std::memcmp(p.offs.data(), offs, sizeof(int64_t) * (T + 1)) == 0) {
+    if (p.uploaded && p.T == T && p.S == S && p.d == d && (int)p.offs.size() == Tb + 1 &&
+        std::memcmp(p.offs.data(), offs, sizeof(int64_t) * (Tb + 1)) == 0) {
       p.stamp = h->clock;
       *out = &p;
       return HB_OK;
@@ -143,18 +148,22 @@ inline int get_plan(hb_handle_t h, int T, const int64_t* offs, int d, cudaStream
   p.uploaded = false;
   for (int& n : p.nitems) n = -1;
   p.T = T;
+  p.S = S;
   p.d = d;
-  p.offs.assign(offs, offs + T + 1);
+  p.offs.assign(offs, offs + Tb + 1);
   p.tasks.resize(T);
   p.nblk_max = 0;
   long long tiles = 0, blocks = 0, chol = 0;
   for (int t = 0; t < T; ++t) {
-    const int64_t n = offs[t + 1] - offs[t];
+    const int tb = t % std::max(Tb, 1);
+    const int64_t n = offs[tb + 1] - offs[tb];
     if (n < 0 || n > (1 << 20)) return fail(h, HB_ERR_BAD_ARG, "bad offs");
     TaskDesc& td = p.tasks[t];
     td.n = (int)n;
     td.nblk = (int)((n + TB - 1) / TB);
-    td.xoff = offs[t];
+    td.xoff = offs[tb];
+    td.theta_idx = Tb > 0 ? t / Tb : 0;
+    td.pad_ = 0;
     td.voff = blocks * TB;
     td.tile_off = tiles;
     td.chol_off = chol;
@@ -165,7 +174,7 @@ inline int get_plan(hb_handle_t h, int T, const int64_t* offs, int d, cudaStream
   }
   p.total_tiles = tiles;
   p.total_blocks = blocks;
-  p.sum_n = offs[T] - offs[0];
+  p.sum_n = (offs[Tb] - offs[0]) * S;
   p.chol_elems = chol;
   const size_t bytes = sizeof(TaskDesc) * (size_t)std::max(T, 1);
   if (bytes > p.tasks_cap) {

@@ -124,6 +124,25 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("generation", [](Handle& s) { return hb_generation(s.h); })
       .def("debug_fused_timeout", [](Handle& s) { return hb_debug_fused_timeout(s.h); })
+      .def("nll_grad_multi",
+           [](Handle& s, int kernel_id, int mean_id, int S, std::vector<int64_t> offs,
+              int d, ptr_t X, ptr_t y, ptr_t raws, uint64_t mask, ptr_t sums,
+              ptr_t nll_task, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_nll_grad_multi(s.h, kernel_id, mean_id, S, (int)offs.size() - 1,
+                                       offs.data(), d, P(X), P(y), P(raws), mask, P(sums),
+                                       P(nll_task), P(stream)), "hb_nll_grad_multi");
+           })
+      .def("build_predictors_multi",
+           [](Handle& s, int kernel_id, int mean_id, int S, int64_t n, int d, ptr_t X,
+              ptr_t y, ptr_t raws, uint64_t mask, ptr_t caches, int64_t stride, ptr_t nll,
+              ptr_t info, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_build_predictors_multi(s.h, kernel_id, mean_id, S, n, d, P(X), P(y),
+                                               P(raws), mask, P(caches), stride, P(nll),
+                                               (int32_t*)P(info), P(stream)),
+                     "hb_build_predictors_multi");
+           })
       .def("subsample",
            [](Handle& s, int T, int d, ptr_t offs_src, ptr_t offs_dst, ptr_t ids,
               int64_t max_rows, ptr_t Xs, ptr_t ys, ptr_t Xd, ptr_t yd, uint64_t seed,

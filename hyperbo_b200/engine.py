@@ -285,6 +285,42 @@ class Engine:
                                float(eps), int(bool(tie_lengthscale)),
                                self._stream())
 
+  # ---- second batch axis: S hyper-parameter sets x the same data -----------
+  def nll_grad_multi(self, kernel_id: int, mean_id: int, ds: PackedDataset, raws,
+                     mask: int, want_task_nll=False):
+    """raws (S, P) -> sums (S, P+2) [+ per-task nll (S, T)]: hb_nll_grad_multi,
+    ONE launch sequence for all S parameter sets."""
+    raws = self.tensor(raws)
+    S, P = int(raws.shape[0]), 3 + ds.d
+    if raws.shape[1] != P:
+      raise ValueError(f"raws must have {P} columns")
+    sums = torch.empty((S, P + 2), device=self.device, dtype=self.dtype)
+    T = ds.num_tasks
+    nll_task = torch.zeros((S, max(T, 1)), device=self.device,
+                           dtype=self.dtype) if want_task_nll else None
+    self.h.nll_grad_multi(kernel_id, mean_id, S, ds.offs, ds.d, ds.x.data_ptr(),
+                          ds.y.data_ptr(), raws.data_ptr(), mask, sums.data_ptr(),
+                          nll_task.data_ptr() if want_task_nll else 0, self._stream())
+    return (sums, nll_task[:, :T]) if want_task_nll else sums
+
+  def build_predictors_multi(self, kernel_id: int, mean_id: int, x, y, raws, mask: int):
+    """S predictor caches of one task from ONE factorisation launch
+    (hb_build_predictors_multi) -> (caches (S, stride) uint8, nll (S,), info (S,))."""
+    x = self.tensor(x)
+    n, d = x.shape
+    self._check_dim(d)
+    y = self.tensor(y).reshape(-1)
+    raws = self.tensor(raws)
+    S = int(raws.shape[0])
+    stride = (int(self.h.predictor_bytes(n)) + 255) // 256 * 256
+    caches = torch.empty((S, stride), device=self.device, dtype=torch.uint8)
+    nll = torch.zeros((S,), device=self.device, dtype=self.dtype)
+    info = torch.zeros((S,), device=self.device, dtype=torch.int32)
+    self.h.build_predictors_multi(kernel_id, mean_id, S, n, d, x.data_ptr(), y.data_ptr(),
+                                  raws.data_ptr(), mask, caches.data_ptr(), stride,
+                                  nll.data_ptr(), info.data_ptr(), self._stream())
+    return caches, nll, info
+
   def adam_step(self, P: int, raw, m, v, accepted, sums, scal, lr, b1=0.9,
                 b2=0.999, eps=1e-8, tie_lengthscale=False):
     self.h.adam_step(P, raw.data_ptr(), m.data_ptr(), v.data_ptr(),

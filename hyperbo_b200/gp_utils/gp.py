@@ -825,8 +825,34 @@ class HGP(GP):
 
   def predict(self, queried_inputs, sub_dataset_key=0, full_cov=False,
               with_noise=True):
+    samples = self.get_model_params_samples()
+    eng = _engine.Engine.get()
+    has_obs = (sub_dataset_key in self.dataset and
+               self.dataset[sub_dataset_key].x.shape[0] > 0)
+    if (not full_cov and has_obs and len(samples) > 1 and
+        getattr(eng, "h", None) is not None):
+      # second batch axis: the S samples' factorisations are ONE launch sequence
+      # (hb_build_predictors_multi); the per-sample predict sweeps reuse it
+      xq = eng.tensor(queried_inputs)
+      kid = _kernel.kernel_id_of(self.cov_func)
+      mid = _mean.mean_id_of(self.mean_func)
+      packs = [params_utils.pack_raw(m, xq.shape[1], mid == 1, self.warp_func)
+               for m in samples]
+      if len({p[1] for p in packs}) == 1:
+        mask = packs[0][1]
+        raws = np.stack([p[0] for p in packs])
+        sd = self.dataset[sub_dataset_key]
+        caches, _, _ = eng.build_predictors_multi(kid, mid, sd.x, sd.y, raws, mask)
+        noise_flag, scale = self._noise_and_scale(with_noise, True)
+        x_obs = eng.tensor(sd.x)
+        out = []
+        for s_ in range(len(samples)):
+          mu, var, _ = eng.predict(kid, mid, x_obs, caches[s_], raws[s_], mask, xq,
+                                   noise_flag=noise_flag, var_scale=scale)
+          out.append((mu, var))
+        return out
     results = []
-    for model_params in self.get_model_params_samples():
+    for model_params in samples:
       self.update_model_params(model_params)
       results.append(super().predict(
           queried_inputs=queried_inputs, sub_dataset_key=sub_dataset_key,

@@ -241,6 +241,28 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
 int hb_acquisition(hb_handle_t h, int acq_id, double acq_param, int64_t nq,
                    const void* mu, const void* var, void* out, void* stream);
 
+/* ---- 8(f) rank 4: S hyper-parameter sets x the same data ---------------- */
+/* The reference evaluates the same dataset under many parameter vectors by
+ * vmapping the whole pipeline (bo_utils/acfun_test.py:74-118, S = 100) or by
+ * looping over HGP samples (gp_utils/gp.py:623-682).  Here the parameter set is
+ * a second batch axis of ONE launch sequence: virtual task (s, t) reads the
+ * data rows of task t and raw_sets[s] ((S, 3+d) row-major).
+ *   hb_nll_grad_multi         : sums_out (S, P+2) as hb_nll_grad_batched per
+ *                               set; nll_task_out_or_null (S, T)
+ *                               (speculative line-search points, HGP stats);
+ *   hb_build_predictors_multi : S predictor caches of one task (cache s at
+ *                               caches + s * cache_stride_bytes, each as
+ *                               hb_build_predictor's), nll_out_or_null (S,). */
+int hb_nll_grad_multi(hb_handle_t h, int kernel_id, int mean_id, int S, int T,
+                      const int64_t* offs_host, int d, const void* X, const void* y,
+                      const void* raw_sets, uint64_t warp_mask, void* sums_out,
+                      void* nll_task_out_or_null, void* stream);
+int hb_build_predictors_multi(hb_handle_t h, int kernel_id, int mean_id, int S, int64_t n,
+                              int d, const void* X, const void* y, const void* raw_sets,
+                              uint64_t warp_mask, void* caches,
+                              int64_t cache_stride_bytes, void* nll_out_or_null,
+                              int32_t* info_out_or_null, void* stream);
+
 /* ---- a11: per-step sub-sampling on the device --------------------------- */
 /* data_utils.sub_sample_dataset_iterator (basics/data_utils.py:72-100): tasks
  * with n >= batch_size are replaced, every step, by batch_size of their points
