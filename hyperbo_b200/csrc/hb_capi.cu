@@ -82,7 +82,7 @@ int hb_create(hb_handle_t* out, int device, int dtype) {
   h->device = device;
   h->dtype = dtype;
   if (const char* e = getenv("HB_PRE")) h->pre_override = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("HB_FUSED")) h->fused = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("HB_FUSED")) h->fused = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("HB_FUSED_GRID")) h->fused_grid = atoi(e);
   if (const char* e = getenv("HB_FUSED_SKEW")) h->fused_skew = atof(e);
   if (const char* e = getenv("HB_FUSED_GROUPS")) h->fused_groups = atoi(e);
@@ -147,6 +147,22 @@ int64_t hb_debug_read(hb_handle_t h, int which, void* host_out, int64_t max_byte
       cudaMemcpy(host_out, bufs[which]->p, nb, cudaMemcpyDeviceToHost) != cudaSuccess)
     return -1;
   return (int64_t)bufs[which]->cap;
+}
+// tuning / test knobs of a handle (the HB_* environment variables set the
+// defaults at hb_create): "fused" 0|1|2, "fastpath" 0|1, "groups", "skew", "grid"
+int hb_set_option(hb_handle_t h, const char* name, double value) {
+  if (!h || !name) return HB_ERR_BAD_ARG;
+  const std::string n(name);
+  if (n == "fused") h->fused = std::max(0, std::min(2, (int)value));
+  else if (n == "fastpath") h->fused_fastpath = value != 0.0;
+  else if (n == "groups") h->fused_groups = (int)value;
+  else if (n == "skew") h->fused_skew = value;
+  else if (n == "grid") h->fused_grid = (int)value;
+  else return fail(h, HB_ERR_BAD_ARG, "unknown option");
+  for (auto& p : h->plans)  // item lists depend on these
+    for (int& k : p.nitems) k = -1;
+  ++h->generation;
+  return HB_OK;
 }
 int hb_debug_fused_timeout(hb_handle_t h) {
   if (!h) return -1;

@@ -60,7 +60,7 @@ struct hb_handle_s {
   bool attr_set = false;
   bool bo_attr_set = false;
   int sm_count = 0;
-  int fused = 1;               // HB_FUSED env: 0 = the launch-per-column path
+  int fused = 1;               // HB_FUSED env: 0 = launch-per-column path, 2 = always persistent
   int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel
   double fused_skew = 0.0;     // HB_FUSED_SKEW env: task skew of the item order
   int fused_fastpath = 1;      // HB_FUSED_FASTPATH env: 0 = acquire-poll every dependency

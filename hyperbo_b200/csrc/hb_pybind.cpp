@@ -171,6 +171,9 @@ PYBIND11_MODULE(_C, m) {
                                 acq_id, acq_param, target_is_ymax, (int32_t*)P(sel),
                                 P(stream)), "hb_bo_step");
            })
+      .def("set_option", [](Handle& s, const std::string& name, double v) {
+             s.check(hb_set_option(s.h, name.c_str(), v), "hb_set_option");
+           })
       .def("debug_read",
            [](Handle& s, int which, ptr_t host_out, int64_t max_bytes) {
              return hb_debug_read(s.h, which, P(host_out), max_bytes);

@@ -83,6 +83,11 @@ int64_t hb_workspace_bytes(hb_handle_t h);
  * engine calls into a CUDA graph must re-capture when it changes (the graph
  * holds raw workspace pointers). */
 int64_t hb_generation(hb_handle_t h);
+/* Tuning / test knobs (defaults come from the HB_* environment variables at
+ * hb_create): "fused" 0 = launch-per-column path, 1 = automatic (persistent
+ * kernel except for few tasks per GPU), 2 = always persistent; "fastpath",
+ * "groups", "skew", "grid" of the persistent kernel's scheduler. */
+int hb_set_option(hb_handle_t h, const char* name, double value);
 /* Debug: synchronises the device and returns 1 if a work item of the persistent
  * kernel ever gave up waiting for a dependency (a scheduling bug), else 0. */
 int hb_debug_fused_timeout(hb_handle_t h);

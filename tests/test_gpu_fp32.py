@@ -48,7 +48,10 @@ def test_golden_fixtures_fp32(eng, name):
   sums = eng.nll_grad(kid, mid, ds, g["raw"], mask).double().cpu().numpy()
   T = len(ns)
   assert sums[-1] == T
-  assert abs(sums[0] / T - g["mean_nll"]) < 2e-5 * abs(g["mean_nll"])
+  # (2e-5 of the SIZE OF THE NLL'S TERMS: with n ~ 100 the value itself nearly
+  # cancels against .5 n log(2 pi), so it is no measure of the arithmetic's scale)
+  scale_nll = abs(g["mean_nll"]) + 0.5 * np.mean(ns) * np.log(2 * np.pi)
+  assert abs(sums[0] / T - g["mean_nll"]) < 2e-5 * scale_nll
   assert H.rel(sums[1:-1] / T, g["grad"]) < 1e-3
   cache, chol, kinvy, _, _ = eng.build_predictor(kid, mid, g["x0"], g["y0"],
                                                  g["raw"], mask)

@@ -30,8 +30,10 @@ def test_nll_grad_multi_equals_sequential_calls(cov):
   sums, nll_task = sums.cpu().numpy(), nll_task.cpu().numpy()
   for s in range(S):
     one, nt = eng.nll_grad(kid, 1, ds, raws[s], mask, want_task_nll=True)
-    assert np.array_equal(sums[s], one.cpu().numpy())       # same kernels, same order
-    assert np.array_equal(nll_task[s], nt.cpu().numpy())
+    # (sequential small calls may take the launch-per-column path, whose sums are
+    # ordered differently: agreement to rounding, not bitwise)
+    assert H.rel(sums[s], one.cpu().numpy()) < 1e-12
+    assert H.rel(nll_task[s], nt.cpu().numpy()) < 1e-12
   # and against the oracle for one of the sets
   m = H.model_from_raw(raws[3], d, "constant")
   v_ref, g_ref = O.nll_value_and_grad("constant", cov, m, ds_np, O.DEFAULT_WARP_FUNC)

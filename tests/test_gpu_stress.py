@@ -11,11 +11,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("T,n,trials", [(8, 512, 40), (32, 512, 40), (48, 300, 40),
-                                        (160, 200, 20)])
-def test_sums_do_not_depend_on_the_previous_call(T, n, trials):
+@pytest.mark.parametrize("path", [2, 1])  # 2: always the persistent kernel; 1: automatic
+@pytest.mark.parametrize("T,n,trials", [(8, 512, 30), (32, 512, 30), (48, 300, 30),
+                                        (160, 200, 15)])
+def test_sums_do_not_depend_on_the_previous_call(T, n, trials, path):
   from hyperbo_b200.engine import Engine
   eng = Engine.get()
+  eng.h.set_option("fused", path)
+  try:
+    _run(eng, T, n, trials)
+  finally:
+    eng.h.set_option("fused", 1)
+
+
+def _run(eng, T, n, trials):
   d = 8
   raw = np.concatenate([[5.1, 0.0, -4.0], np.linspace(-0.3, 0.4, d)])
   mask = 0b110 | (((1 << d) - 1) << 3)
