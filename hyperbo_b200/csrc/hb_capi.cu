@@ -29,6 +29,8 @@ using namespace hb::host;
                        const void*, void*, void*);
 namespace hb {
 #define HB_COMM_PROTOTYPES                                                      \
+  int64_t debug_items_impl(hb_handle_t, int, const int64_t*, int, int,          \
+                           int32_t*, int64_t);                                  \
   int nll_grad_multi_impl(hb_handle_t, int, int, int, int, const int64_t*, int, \
                           const void*, const void*, const void*, uint64_t,      \
                           void*, void*, void*);                                 \
@@ -163,6 +165,12 @@ int hb_set_option(hb_handle_t h, const char* name, double value) {
     for (int& k : p.nitems) k = -1;
   ++h->generation;
   return HB_OK;
+}
+int64_t hb_debug_items(hb_handle_t h, int T, const int64_t* offs, int d, int variant,
+                       int32_t* out, int64_t max_items) {
+  if (!h) return -1;
+  return h->dtype == HB_F64 ? hb::f64::debug_items_impl(h, T, offs, d, variant, out, max_items)
+                            : hb::f32::debug_items_impl(h, T, offs, d, variant, out, max_items);
 }
 int hb_debug_fused_timeout(hb_handle_t h) {
   if (!h) return -1;

@@ -171,6 +171,15 @@ PYBIND11_MODULE(_C, m) {
                                 acq_id, acq_param, target_is_ymax, (int32_t*)P(sel),
                                 P(stream)), "hb_bo_step");
            })
+      .def("debug_items",
+           [](Handle& s, std::vector<int64_t> offs, int d, int variant) {
+             int64_t n = hb_debug_items(s.h, (int)offs.size() - 1, offs.data(), d, variant,
+                                        nullptr, 0);
+             std::vector<int32_t> out((size_t)std::max<int64_t>(n, 0) * 4);
+             if (n > 0)
+               hb_debug_items(s.h, (int)offs.size() - 1, offs.data(), d, variant, out.data(), n);
+             return out;
+           })
       .def("set_option", [](Handle& s, const std::string& name, double v) {
              s.check(hb_set_option(s.h, name.c_str(), v), "hb_set_option");
            })

@@ -88,6 +88,12 @@ int64_t hb_generation(hb_handle_t h);
  * kernel except for few tasks per GPU), 2 = always persistent; "fastpath",
  * "groups", "skew", "grid" of the persistent kernel's scheduler. */
 int hb_set_option(hb_handle_t h, const char* name, double value);
+/* Debug / tests: the persistent kernel's work-item order for a batch shape:
+ * out receives (task, kind, a, b) per item (kind 0 DIAG, 1 PANEL, 2 TRTRI,
+ * 3 LAUUM, 4 ALPHA); variant 0 factor, 1 + inverse, 2 + gradient.  Returns the
+ * number of items.  The order must be a topological order of the tile DAG. */
+int64_t hb_debug_items(hb_handle_t h, int T, const int64_t* offs_host, int d, int variant,
+                       int32_t* out, int64_t max_items);
 /* Debug: synchronises the device and returns 1 if a work item of the persistent
  * kernel ever gave up waiting for a dependency (a scheduling bug), else 0. */
 int hb_debug_fused_timeout(hb_handle_t h);
