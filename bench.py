@@ -480,16 +480,26 @@ def run_ours(args):
       traffic = None
 
   # the dominant kernel IS the step: one persistent launch (k_fused) computes
-  # kernel tiles, Cholesky, inverse, alpha and the gradient contraction
+  # kernel tiles, Cholesky, inverse, alpha and the gradient contraction.  (With
+  # few tasks per GPU the launch-per-column path runs instead: the dominant
+  # group is then its k_step launches.)
   ms_fused = prof_ms[2] / max(prof_cnt[2], 1)
-  ach = fl["step"] / ms_fused / 1e9
+  persistent = R["launches_per_step"] <= 6
+  if persistent:
+    dom_ms, dom_fl = ms_fused, fl["step"]
+    dom_name = ("k_fused (persistent, dependency-driven: kernel-matrix tiles + blocked "
+                "Cholesky + triangular inverse + alpha + K~^-1 tiles with the gradient "
+                "contraction) -- the dominant kernel, ~98% of the step")
+  else:
+    dom_ms, dom_fl = prof_ms[0] / max(prof_cnt[0], 1), fl["factor_launches"]
+    dom_name = ("k_step x (nblk+1) launches (few tasks per GPU: launch-per-column path): "
+                "kernel build + blocked Cholesky + triangular inverse")
+  ach = dom_fl / dom_ms / 1e9
   roofline = {
       "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-      "frac": ach / peak_tf, "ms_per_launch": ms_fused, "traffic": traffic,
-      "kernel": "k_fused (persistent, dependency-driven: kernel-matrix tiles + "
-                "blocked Cholesky + triangular inverse + alpha + K~^-1 tiles with "
-                "the gradient contraction) -- the dominant kernel, ~98% of the step",
-      "peak_source": peak_source, "flops_per_launch": fl["step"],
+      "frac": ach / peak_tf, "ms_per_launch": dom_ms, "traffic": traffic,
+      "kernel": dom_name,
+      "peak_source": peak_source, "flops_per_launch": dom_fl,
       "algorithmic_flops": "SURVEY 8(d): T (n^3 + 4 n^2 + n^2 (3d+8) + n^2 (2d+6))"}
   roofline_step = {
       "bound": "tensor", "achieved": fl["step"] / ms_step / 1e9,
@@ -548,11 +558,16 @@ def run_ours(args):
       "roofline": roofline,
       "roofline_step": roofline_step,
       "cholesky": cholesky,
-      "section_ms_per_step": {
-          "prep": prof_ms[0] / max(prof_cnt[0], 1),
-          "k_fused": ms_fused,
-          "task_final": prof_ms[1] / max(prof_cnt[1], 1),
-          "reduce": prof_ms[3] / max(prof_cnt[3], 1)},
+      "section_ms_per_step": (
+          {"path": "persistent kernel", "prep": prof_ms[0] / max(prof_cnt[0], 1),
+           "k_fused": ms_fused, "task_final": prof_ms[1] / max(prof_cnt[1], 1),
+           "reduce": prof_ms[3] / max(prof_cnt[3], 1)}
+          if R["launches_per_step"] <= 6 else
+          {"path": "launch per block column (few tasks per GPU)",
+           "prep+k_step": prof_ms[0] / max(prof_cnt[0], 1),
+           "k_alpha": prof_ms[1] / max(prof_cnt[1], 1),
+           "k_lauum_grad": ms_fused,
+           "reduce": 2 * prof_ms[3] / max(prof_cnt[3], 1)}),
       "subsampled_training": subsampled,
       "other_precision": other,
       "cpu_baseline": cpu,
