@@ -55,6 +55,25 @@ def main():
     print(f"role {role}: launch rc={rc}  max rel err vs fp32 = {err:.3e} "
           f"(TF32 inputs: expect ~1e-3)")
     ok = ok and rc == 0 and err < 5e-3
+  # MN-major descriptor variants (role 1): which (LBO, SBO, K step) describes the
+  # packed tile read as [k][mn]?
+  a = rng.standard_normal((64, 64)).astype(np.float32)
+  b = rng.standard_normal((64, 64)).astype(np.float32)
+  want = a.T @ b
+  ta, tb = torch.from_numpy(pack(a)).cuda(), torch.from_numpy(pack(b)).cuda()
+  for lbo, sbo, kstep in ((2048, 128, 2048), (128, 2048, 2048), (128, 1024, 2048),
+                          (1024, 128, 2048), (2048, 128, 1024), (128, 2048, 1024),
+                          (128, 128, 2048), (2048, 2048, 2048), (4096, 128, 2048),
+                          (128, 4096, 2048), (256, 2048, 2048), (2048, 256, 2048)):
+    d = torch.zeros((64, 64), dtype=torch.float32, device="cuda")
+    rc = lib.hb_exp_umma_tf32_tile_mn(ctypes.c_void_p(ta.data_ptr()), ctypes.c_void_p(tb.data_ptr()),
+                                      ctypes.c_void_p(d.data_ptr()), lbo, sbo, kstep, None)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy()
+    err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+    # how many output entries are right: hints at which dimension is mis-strided
+    good = float(np.mean(np.abs(got - want) < 2e-2 * np.max(np.abs(want))))
+    print(f"MN variant lbo={lbo} sbo={sbo} kstep={kstep}: rc={rc} err={err:.3e} good={good:.2f}")
   return 0 if ok else 1
 
 

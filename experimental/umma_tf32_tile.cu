@@ -65,7 +65,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 
 __global__ void __launch_bounds__(256) k_umma_tile(const float* __restrict__ A,
                                                    const float* __restrict__ B,
-                                                   float* __restrict__ D, int role) {
+                                                   float* __restrict__ D, int role,
+                                                   unsigned lbo_mn, unsigned sbo_mn,
+                                                   unsigned kstep_mn) {
   __shared__ __align__(128) float sA[TILE_ELEMS];
   __shared__ __align__(128) float sB[TILE_ELEMS];
   __shared__ __align__(8) uint64_t bar;
@@ -100,8 +102,8 @@ __global__ void __launch_bounds__(256) k_umma_tile(const float* __restrict__ A,
     // MN-major role: next 4 MN columns = next col-block (128 B) = SBO;
     //                next 8 K rows = next row-block (2048 B) = LBO;
     //                K advances by 8 rows = one row-block = 2048 B per instruction.
-    const uint32_t lbo = role ? 2048u : 128u, sbo = role ? 128u : 2048u;
-    const uint32_t kstep = role ? 2048u : 256u;
+    const uint32_t lbo = role ? lbo_mn : 128u, sbo = role ? sbo_mn : 2048u;
+    const uint32_t kstep = role ? kstep_mn : 256u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint64_t da = make_desc(smem_u32(sA) + k * kstep, lbo, sbo);
@@ -162,6 +164,13 @@ __global__ void __launch_bounds__(256) k_umma_tile(const float* __restrict__ A,
 // D: device pointer to 64 x 64 row-major floats.  role: 0 K-major, 1 MN-major.
 extern "C" int hb_exp_umma_tf32_tile(const float* A_tile, const float* B_tile, float* D,
                                      int role, void* stream) {
-  k_umma_tile<<<1, 256, 0, (cudaStream_t)stream>>>(A_tile, B_tile, D, role);
+  k_umma_tile<<<1, 256, 0, (cudaStream_t)stream>>>(A_tile, B_tile, D, role, 2048u, 128u, 2048u);
+  return (int)cudaGetLastError();
+}
+// MN-major descriptor experiments: explicit LBO / SBO / per-instruction K step
+extern "C" int hb_exp_umma_tf32_tile_mn(const float* A_tile, const float* B_tile, float* D,
+                                        unsigned lbo, unsigned sbo, unsigned kstep,
+                                        void* stream) {
+  k_umma_tile<<<1, 256, 0, (cudaStream_t)stream>>>(A_tile, B_tile, D, 1, lbo, sbo, kstep);
   return (int)cudaGetLastError();
 }

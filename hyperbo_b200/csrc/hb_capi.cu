@@ -56,9 +56,22 @@ namespace f32 { HB_IMPL_PROTOTYPES HB_COMM_PROTOTYPES }
 }  // namespace hb
 #undef HB_IMPL_PROTOTYPES
 
+// Every compute entry point: serialise on the handle (its plan cache, workspace
+// and error string are shared state) and run on the handle's device whatever
+// device is current in the calling thread.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 #define HB_DISPATCH(fn, ...)                                          \
   do {                                                                \
     if (!h) return HB_ERR_BAD_ARG;                                    \
+    std::lock_guard<std::recursive_mutex> lock_(h->mu);               \
+    DeviceGuard guard_(h->device);                                    \
     return h->dtype == HB_F64 ? hb::f64::fn(__VA_ARGS__)              \
                               : hb::f32::fn(__VA_ARGS__);             \
   } while (0)

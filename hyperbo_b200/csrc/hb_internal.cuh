@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,7 @@ constexpr int NPLAN = 4;
 }  // namespace hb
 
 struct hb_handle_s {
+  std::recursive_mutex mu;  // entry points serialise on the handle
   int device = 0;
   int dtype = HB_F64;
   std::string err;
