@@ -127,6 +127,29 @@ class Engine:
     """tasks: iterable of (key, x (n,d), y (n,1) or (n,)).  Empty tasks are
     dropped (objectives.py:184 of the reference)."""
     keys, xs, ys, offs = [], [], [], [0]
+    tasks = list(tasks)
+    if tasks and all(not isinstance(x, torch.Tensor) and not isinstance(y, torch.Tensor)
+                     for _, x, y in tasks):
+      # host arrays: concatenate on the host, ONE upload per array (a batch of
+      # 256 tasks would otherwise be 512 small host->device copies)
+      hx, hy = [], []
+      for k, x, y in tasks:
+        x = np.asarray(x, dtype=np.float64)
+        if x.shape[0] == 0:
+          continue
+        y = np.asarray(y, dtype=np.float64).reshape(-1)
+        if y.shape[0] != x.shape[0]:
+          raise ValueError(f"dataset[{k}].x has shape {tuple(x.shape)} but y has "
+                           f"{y.shape[0]} rows")
+        keys.append(k)
+        hx.append(x)
+        hy.append(y)
+        offs.append(offs[-1] + x.shape[0])
+      if hx:
+        x = self.tensor(np.concatenate(hx, 0))
+        self._check_dim(x.shape[1])
+        return PackedDataset(keys, x, self.tensor(np.concatenate(hy, 0)), offs)
+      tasks = []
     for k, x, y in tasks:
       x = self.tensor(x)
       if x.shape[0] == 0:

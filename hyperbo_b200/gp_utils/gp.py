@@ -488,16 +488,29 @@ def infer_parameters(mean_func,
 
 def sample_from_gp(key, mean_func, cov_func, params, x, warp_func=None,
                    num_samples=1, method="cholesky", eps=1e-6):
-  """Sample functions from a GP at x (gp.py:198-239): mean + chol(K+noise+eps) z."""
+  """Sample functions from a GP at x (gp.py:198-239): mean + chol(K+noise+eps) z.
+
+  The factor comes from the engine (hb_factorize_batched on one pseudo task at
+  the reference's jitter eps = 1e-6, linalg.py:42; another eps falls back to an
+  explicit-matrix Cholesky)."""
   del method
-  n = torch.as_tensor(x).shape[0]
-  _, cov = linalg.compute_delta_y_and_cov(
-      mean_func, cov_func, params, x, torch.zeros((n, 1)), warp_func, eps)
+  eng = _engine.Engine.get()
+  xt = eng.tensor(x)
+  n, d = xt.shape
   gen = key if isinstance(key, torch.Generator) else torch.Generator().manual_seed(
       int(key) if key is not None else 0)
-  z = torch.randn((cov.shape[0], num_samples), generator=gen,
-                  dtype=torch.float64).to(cov.device)
-  mean = mean_func(params, x, warp_func=warp_func).to(cov.device)
+  z = torch.randn((n, num_samples), generator=gen, dtype=torch.float64).to(
+      device=eng.device, dtype=eng.dtype)
+  mean = eng.tensor(mean_func(params, x, warp_func=warp_func))
+  if eps == _engine.JITTER and getattr(eng, "h", None) is not None and n > 0:
+    kid = _kernel.kernel_id_of(cov_func)
+    raw, mask, _ = params_utils.pack_raw(params.model, d, False, warp_func)
+    ds = eng.pack([(0, xt, torch.zeros((n,), device=eng.device, dtype=eng.dtype))])
+    chols, _, _, _ = eng.factorize(kid, 0, ds, raw, mask, want_chol=True,
+                                   want_alpha=False)
+    return mean + chols[0] @ z
+  _, cov = linalg.compute_delta_y_and_cov(
+      mean_func, cov_func, params, x, torch.zeros((n, 1)), warp_func, eps)
   return mean + torch.linalg.cholesky(cov) @ z
 
 

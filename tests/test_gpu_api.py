@@ -363,3 +363,18 @@ def test_acfun_over_hyperparameter_sets(name):
                          xq, None)
     assert np.max(np.abs(_np(evals[s]) - want)) < 1e-6 * (
         np.max(np.abs(want)) + 1e-3), (name, s)
+
+
+def test_sample_from_gp_uses_the_engine_factor():
+  """gp.py:198-239: mean + chol(K + (noise + 1e-6) I) z -- the factor now comes
+  from hb_factorize_batched; same draw as the explicit-matrix Cholesky."""
+  truth = defs.GPParams(model={"constant": 5.0, "lengthscale": 1.0,
+                               "signal_variance": 1.0, "noise_variance": 0.01})
+  vx = np.random.default_rng(5).random((150, 3))
+  got = _np(gp.sample_from_gp(7, mean.constant, kernel.matern52, truth, vx, num_samples=4))
+  _, cov = linalg.compute_delta_y_and_cov(mean.constant, kernel.matern52, truth, vx,
+                                          torch.zeros((150, 1)), None, 1e-6)
+  z = torch.randn((150, 4), generator=torch.Generator().manual_seed(7), dtype=torch.float64)
+  want = 5.0 + _np(torch.linalg.cholesky(cov)) @ z.numpy()
+  assert got.shape == (150, 4)
+  assert np.max(np.abs(got - want)) < 1e-9 * np.max(np.abs(want))
