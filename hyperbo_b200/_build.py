@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> None:
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
   cu_src = [os.path.join(CSRC, f) for f in UNITS + (
       "hb_internal.cuh", "hb_common.cuh", "hb_device.inc", "hb_kernels.inc",
-      "hb_host.inc")]
+      "hb_host.inc", "hb_fused.inc", "hb_mrhs.inc")]
   hdr = os.path.join(HERE, "..", "include", "hyperbo_b200.h")
   if force or _newer(LIB, cu_src + [hdr]):
     # objects go to a scratch directory: only the linked .so stays in-tree

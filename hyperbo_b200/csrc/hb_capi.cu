@@ -48,6 +48,10 @@ namespace hb {
                    const void*, double, double, int, double, int, int32_t*,     \
                    void*);                                                      \
   int fused_timeout_impl();                                                     \
+  int nll_grad_mrhs_impl(hb_handle_t, int, int, int, const int64_t*, int,       \
+                         const void*, int, const void*, const void*,            \
+                         const int32_t*, const void*, uint64_t, const void*,    \
+                         double, void*, int32_t*, void*);                       \
   int allreduce_impl(hb_handle_t, void*, int, void*);                           \
   int allreduce_adam_impl(hb_handle_t, int, void*, void*, void*, void*, void*,  \
                           void*, double, double, double, double, int, void*);
@@ -134,7 +138,8 @@ int hb_destroy(hb_handle_t h) {
   Buf* all[] = {&h->theta, &h->Lt,    &h->Mt,  &h->Wt, &h->zz,  &h->z,    &h->alpha,
                 &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                 &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
-                &h->vpart, &h->pcache, &h->pre, &h->sync, &h->apart};
+                &h->vpart, &h->pcache, &h->pre, &h->sync, &h->apart,
+                &h->mrz,   &h->mra,    &h->zeros};
   for (auto* b : all)
     if (b->p) cudaFree(b->p);
   for (auto& p : h->plans) {
@@ -316,6 +321,16 @@ int hb_nll_grad_weighted(hb_handle_t h, int kernel_id, int mean_id, int T,
                          void* nll_task_out, int32_t* info_out, void* stream) {
   HB_DISPATCH(nll_grad_batched_impl, h, kernel_id, mean_id, T, offs, d, X, y,
               raw, warp_mask, task_weight, jitter, sums_out, nll_task_out,
+              info_out, stream);
+}
+
+int hb_nll_grad_mrhs(hb_handle_t h, int kernel_id, int mean_id, int T,
+                     const int64_t* offs, int d, const void* X, int R,
+                     const void* B, const void* col_weight, const int32_t* col_mean,
+                     const void* raw, uint64_t warp_mask, const void* task_weight,
+                     double jitter, void* sums_out, int32_t* info_out, void* stream) {
+  HB_DISPATCH(nll_grad_mrhs_impl, h, kernel_id, mean_id, T, offs, d, X, R, B,
+              col_weight, col_mean, raw, warp_mask, task_weight, jitter, sums_out,
               info_out, stream);
 }
 

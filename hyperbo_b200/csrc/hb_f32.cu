@@ -14,5 +14,6 @@ __device__ __forceinline__ Real2 make_real2(Real a, Real b) { return make_float2
 #include "hb_kernels.inc"
 #include "hb_fused.inc"
 #include "hb_host.inc"
+#include "hb_mrhs.inc"
 }  // namespace f32
 }  // namespace hb

@@ -112,6 +112,19 @@ PYBIND11_MODULE(_C, m) {
                          P(stream)),
                      "hb_nll_grad_weighted");
            })
+      .def("nll_grad_mrhs",
+           [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
+              int d, ptr_t X, int R, ptr_t B, ptr_t col_w, ptr_t col_mean, ptr_t raw,
+              uint64_t mask, ptr_t weight, double jitter, ptr_t sums, ptr_t info,
+              ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_nll_grad_mrhs(
+                         s.h, kernel_id, mean_id, (int)offs.size() - 1,
+                         offs.data(), d, P(X), R, P(B), P(col_w),
+                         (const int32_t*)P(col_mean), P(raw), mask, P(weight),
+                         jitter, P(sums), (int32_t*)P(info), P(stream)),
+                     "hb_nll_grad_mrhs");
+           })
       .def("adam_step",
            [](Handle& s, int np, ptr_t raw, ptr_t mm, ptr_t vv, ptr_t accepted,
               ptr_t sums, ptr_t scal, double lr, double b1, double b2, double eps,

@@ -255,6 +255,40 @@ class Engine:
       return sums_out, nll_task[:T]
     return sums_out
 
+  def nll_grad_mrhs(self, kernel_id: int, mean_id: int, ds: PackedDataset, R: int,
+                    B: torch.Tensor, col_weight: torch.Tensor,
+                    col_mean: Optional[torch.Tensor], raw, mask: int,
+                    weights: Optional[torch.Tensor] = None,
+                    jitter: Optional[float] = None,
+                    sums_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """hb_nll_grad_mrhs: R right-hand-side columns per task on ONE factorisation
+    of each task's inputs (ds.y is not read).  B: flat, task t owns the (R, n_t)
+    block at offs[t] * R with every column contiguous; col_weight (T, R);
+    col_mean (R,) int32 (1: subtract the model mean from that column)."""
+    raw = self.tensor(raw)
+    T = ds.num_tasks
+    if sums_out is None:
+      sums_out = torch.empty((3 + ds.d + 2,), device=self.device, dtype=self.dtype)
+    B = self.tensor(B).reshape(-1)
+    col_weight = self.tensor(col_weight).reshape(-1)
+    if B.shape[0] != ds.offs[-1] * R or col_weight.shape[0] != T * R:
+      raise ValueError("B / col_weight do not match the (tasks, R) layout")
+    if col_mean is not None:
+      col_mean = torch.as_tensor(col_mean, device=self.device).to(torch.int32)
+      if col_mean.shape[0] != R:
+        raise ValueError("col_mean needs R entries")
+    if weights is not None:
+      weights = self.tensor(weights).reshape(-1)
+      if weights.shape[0] != T:
+        raise ValueError(f"weights has {weights.shape[0]} entries for {T} tasks")
+    self.h.nll_grad_mrhs(
+        kernel_id, mean_id, ds.offs, ds.d, ds.x.data_ptr(), R, B.data_ptr(),
+        col_weight.data_ptr(), col_mean.data_ptr() if col_mean is not None else 0,
+        raw.data_ptr(), mask, weights.data_ptr() if weights is not None else 0,
+        JITTER if jitter is None else float(jitter), sums_out.data_ptr(), 0,
+        self._stream())
+    return sums_out
+
   def generation(self) -> int:
     """Bumped whenever a workspace buffer / cached plan of the handle moves:
     CUDA graphs that captured engine calls must be re-captured then."""

@@ -176,7 +176,9 @@ nll = neg_log_marginal_likelihood
 #          = 2 sum_q nll0(Yc_q) + 2 nll_m(mu0) - 2 m nll0(0) - n log 2pi
 #          where nll0 / nll_m are the per-task NLL with zero / the model's mean
 #          function and jitter = eps:  m + 2 tasks that share x.  The gradient
-#          is the same weighted sum of the per-task gradients.
+#          is the same weighted sum of the per-task gradients.  By default the
+#          m + 1 residual columns [Yc | mu0 - m(x)] ride on ONE factorisation of
+#          x (hb_nll_grad_mrhs, _LaunchMRHS) instead of m + 2 of them.
 # ---------------------------------------------------------------------------
 class _Launch:
   """One weighted engine call: value/grad sums are scaled by `scale`."""
@@ -184,6 +186,21 @@ class _Launch:
   def __init__(self, ds, mean_id, weights, jitter, scale):
     self.ds, self.mean_id, self.weights = ds, mean_id, weights
     self.jitter, self.scale = jitter, scale
+
+
+class _LaunchMRHS:
+  """One hb_nll_grad_mrhs call: aligned sub-datasets with the same number of
+  columns, R = m + 1 right-hand sides on ONE factorisation of each x."""
+
+  def __init__(self, ds, mean_id, R, B, col_w, col_mean, weights, jitter):
+    self.ds, self.mean_id, self.R, self.B = ds, mean_id, R, B
+    self.col_w, self.col_mean, self.weights = col_w, col_mean, weights
+    self.jitter, self.scale = jitter, 1.0
+
+
+# False: the partial KL runs as m + 2 weighted NLL tasks that share x (the
+# round-1 decomposition, kept as a cross-check of the multi-RHS entry)
+KL_MULTI_RHS = True
 
 
 class ObjectiveProgram:
@@ -211,8 +228,13 @@ class ObjectiveProgram:
       out = torch.empty(self.P + 2, device=eng.device, dtype=eng.dtype)
     out.zero_()
     for l in self.launches:
-      s = eng.nll_grad(self.kid, l.mean_id, l.ds, raw, mask, weights=l.weights,
-                       jitter=l.jitter)
+      if isinstance(l, _LaunchMRHS):
+        s = eng.nll_grad_mrhs(self.kid, l.mean_id, l.ds, l.R, l.B, l.col_w,
+                              l.col_mean, raw, mask, weights=l.weights,
+                              jitter=l.jitter)
+      else:
+        s = eng.nll_grad(self.kid, l.mean_id, l.ds, raw, mask, weights=l.weights,
+                         jitter=l.jitter)
       out[:self.P + 1].add_(s[:self.P + 1], alpha=l.scale)
     for scale, ds, eps in self.trace_terms:
       # tr(K1^-1) = 2 d nll0(0)/d noise_variance (un-chained)
@@ -272,8 +294,10 @@ def _aligned_subs(dataset):
   return out
 
 
-def _shard(items, rank, world):
-  return [it for t, it in enumerate(items) if t % world == rank]
+def _shard(items, rank, world, start=0):
+  """Round-robin share of `rank`; `start` continues the rotation of the
+  previous launch so that several short launches do not all land on rank 0."""
+  return [it for t, it in enumerate(items) if (start + t) % world == rank]
 
 
 def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
@@ -283,6 +307,7 @@ def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
   mid = _mean.mean_id_of(mean_func)
   eng = _engine.Engine.get()
   launches, const, trace_terms, d = [], 0.0, [], None
+  rr = 0  # tasks handed out so far (rotation of the round-robin sharding)
 
   def pack_weighted(tasks, mean_id, jitter):
     """tasks: [(x, y, w)] -> launch with per-task weights (scale 1)."""
@@ -298,7 +323,8 @@ def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
       items = _select(dataset, exclude_aligned=True)
       if not items:
         continue
-      ds = eng.pack(_shard(items, rank, world))
+      ds = eng.pack(_shard(items, rank, world, rr))
+      rr += len(items)
       launches.append(_Launch(ds, mid, None, None, coef / len(items)))
       d = d or int(torch.as_tensor(items[0][1]).shape[1])
     elif kind == "kl":
@@ -312,19 +338,39 @@ def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
         continue
       c = coef * float(kw.get("weight", 1.0)) / len(subs)
       zero_mean_tasks, model_mean_tasks, zero_tasks = [], [], []
-      for _, x, y in subs:
+      by_m = {}
+      for si, (_, x, y) in enumerate(subs):
         x, y = eng.tensor(x), eng.tensor(y)
         n, m = y.shape
         d = d or int(x.shape[1])
         mu0 = y.mean(dim=1)
         yc = (y - mu0[:, None]) / math.sqrt(m)
-        for q in range(m):
-          zero_mean_tasks.append((x, yc[:, q], 2.0 * c))
         zeros = torch.zeros_like(mu0)
-        zero_mean_tasks.append((x, zeros, -2.0 * m * c))
-        model_mean_tasks.append((x, mu0, 2.0 * c))
         zero_tasks.append((x, zeros, 1.0))
         const -= c * n * math.log(2 * math.pi)
+        if KL_MULTI_RHS:
+          if (rr + si) % world == rank:
+            by_m.setdefault(m, []).append((x, yc, mu0))
+          continue
+        for q in range(m):
+          zero_mean_tasks.append((x, yc[:, q], 2.0 * c))
+        zero_mean_tasks.append((x, zeros, -2.0 * m * c))
+        model_mean_tasks.append((x, mu0, 2.0 * c))
+      # one factorisation per sub-dataset: B = [Yc / sqrt(m) | mu_data], the last
+      # column against the model mean (hb_nll_grad_mrhs)
+      rr += len(subs) if KL_MULTI_RHS else 0
+      for m, mine in by_m.items():
+        ds = eng.pack([(i, x, torch.zeros_like(mu0)) for i, (x, _, mu0) in
+                       enumerate(mine)])
+        B = torch.cat([torch.cat([yc.T.reshape(-1), mu0]) for _, yc, mu0 in mine])
+        R = m + 1
+        col_w = torch.full((len(mine), R), 2.0 * c, device=eng.device,
+                           dtype=eng.dtype)
+        col_mean = torch.zeros(R, dtype=torch.int32, device=eng.device)
+        col_mean[m] = 1
+        wts = torch.full((len(mine),), 2.0 * c, device=eng.device, dtype=eng.dtype)
+        launches.append(_LaunchMRHS(ds, mid, R, B.contiguous(), col_w, col_mean,
+                                    wts, eps))
       if mid == 0:
         zero_mean_tasks += model_mean_tasks
         model_mean_tasks = []

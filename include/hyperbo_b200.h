@@ -181,6 +181,30 @@ int hb_nll_grad_weighted(hb_handle_t h, int kernel_id, int mean_id, int T,
                          void* sums_out, void* nll_task_out_or_null,
                          int32_t* info_out_or_null, void* stream);
 
+/* Several right-hand sides on ONE factorisation per task: the same objective
+ * family as hb_nll_grad_weighted without refactorising X once per column.
+ *   B          : task t owns the (R, n_t) block at element offset offs[t] * R,
+ *                column q contiguous (column-major per task);
+ *   col_weight : (T, R) device scalars c_tq;
+ *   col_mean_or_null : (R) device int32, 1 = subtract the model mean m(x)
+ *                (mean_id) from column q, 0 = use the column as it is;
+ *   task_weight_or_null : (T,) device scalars w_t (1 if null).
+ *   sums_out[0]   = sum_t { w_t (sum_i log L_ii + .5 n_t log 2pi)
+ *                           + sum_q c_tq .5 r_tq' K~_t^-1 r_tq },
+ *   sums_out[1+p] = d sums_out[0] / d raw_p,   sums_out[1+P] = task count.
+ * The partial KL of utils.kl_multivariate_normal (gp_utils/utils.py:84-106) on
+ * an aligned sub-dataset with m columns is the call with R = m + 1,
+ * B = [Yc / sqrt(m) | mu_data], col_mean = [0,...,0,1], w_t = c_tq = 2 (x the
+ * term's weight), minus n log 2pi: one Cholesky / inverse per sub-dataset
+ * instead of the m + 2 of the hb_nll_grad_weighted decomposition. */
+int hb_nll_grad_mrhs(hb_handle_t h, int kernel_id, int mean_id, int T,
+                     const int64_t* offs_host, int d, const void* X, int R,
+                     const void* B, const void* col_weight,
+                     const int32_t* col_mean_or_null, const void* raw,
+                     uint64_t warp_mask, const void* task_weight_or_null,
+                     double jitter, void* sums_out, int32_t* info_out_or_null,
+                     void* stream);
+
 /* ---- a11: one optax.adam update (gp_utils/gp.py:124,143-144) ------------ */
 /* state (device, handle dtype): raw[P], m[P], v[P], accepted[P].
  * scalars_io (device, 4 scalars): [0] loss of this step (written),

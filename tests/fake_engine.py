@@ -86,6 +86,56 @@ class FakeEngine(_engine.Engine):
     return res
 
 
+  def nll_grad_mrhs(self, kernel_id, mean_id, ds, R, B, col_weight, col_mean, raw,
+                    mask, weights=None, jitter=None, sums_out=None):
+    """hb_nll_grad_mrhs contract, written out directly (dense inverse): one K~ per
+    task, R residual columns, value and raw-parameter gradient."""
+    raw = self._np(raw)
+    jitter = O.JITTER if jitter is None else float(jitter)
+    T, d = ds.num_tasks, ds.d
+    P = 3 + d
+    warped = np.array([(mask >> p) & 1 for p in range(P)], dtype=bool)
+    theta = np.where(warped, O.softplus(raw) + O.EPS_WARP, raw)
+    chain = np.where(warped, O.sigmoid(raw), 1.0)
+    c = theta[0] if mean_id == 1 else 0.0
+    sv, nv, ls = theta[1], theta[2], theta[3:]
+    name = _KERNELS[kernel_id]
+    B = self._np(B).reshape(-1)
+    cw = self._np(col_weight).reshape(T, R)
+    cm = np.zeros(R) if col_mean is None else self._np(col_mean).reshape(R)
+    w = np.ones(T) if weights is None else self._np(weights).reshape(T)
+    out = np.zeros(P + 2)
+    x = ds.x.numpy()
+    for t in range(T):
+      lo, hi = ds.offs[t], ds.offs[t + 1]
+      n = hi - lo
+      if n == 0:
+        continue
+      xt = x[lo:hi]
+      res = B[lo * R:hi * R].reshape(R, n).T - c * cm[None, :]   # (n, R)
+      r2, diff = O._scaled_sqdist(xt, xt, ls)  # pylint: disable=protected-access
+      k = O._kernel_from_r2(name, r2, sv)  # pylint: disable=protected-access
+      chol = np.linalg.cholesky(k + np.eye(n) * (nv + jitter))
+      kinv = spla.cho_solve((chol, True), np.eye(n))
+      a = kinv @ res
+      out[0] += w[t] * (np.sum(np.log(np.diag(chol))) + 0.5 * n * math.log(2 * math.pi))
+      out[0] += 0.5 * np.sum(cw[t] * np.sum(res * a, axis=0))
+      g = 0.5 * (w[t] * kinv - (a * cw[t][None, :]) @ a.T)
+      pw = O._pair_weight(name, r2, k, sv)  # pylint: disable=protected-access
+      grad = np.zeros(P)
+      grad[0] = -float(np.sum(cw[t] * cm * np.sum(a, axis=0))) if mean_id == 1 else 0.0
+      grad[1] = float(np.sum(g * k) / sv)
+      grad[2] = float(np.trace(g))
+      grad[3:] = np.einsum("ij,ijk->k", g * pw, diff * diff) / ls
+      out[1:-1] += grad * chain
+      out[-1] += 1.0
+    self.calls += 1
+    res_t = torch.from_numpy(out)
+    if sums_out is not None:
+      sums_out.copy_(res_t)
+      res_t = sums_out
+    return res_t
+
   # ---- the rest of the Engine surface (same contracts as engine.py) ---------
   @staticmethod
   def _np(a):

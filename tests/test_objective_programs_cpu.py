@@ -73,11 +73,15 @@ def test_combined_objective_program(monkeypatch):
   objective = objectives.add(objectives.nll, objectives.mul(0.3, objectives.regkl))
   prog = objectives.compile_objective(objective, mean.constant, kernel.matern52,
                                       dataset)
-  # nll launch + zero-mean kl launch + model-mean kl launch
-  assert len(prog.launches) == 3 and prog.has_exact_grad
+  # nll launch + ONE multi-right-hand-side kl launch (one factorisation per
+  # aligned sub-dataset)
+  # (sub-datasets with the same number of columns share a launch)
+  n_m = len({int(y.shape[1]) for _, _, y in objectives._aligned_subs(dataset)})
+  assert len(prog.launches) == 1 + n_m and prog.has_exact_grad
+  assert all(isinstance(l, objectives._LaunchMRHS) for l in prog.launches[1:])
   raw, mask, _ = params_utils.pack_raw(params.model, g["d"], True, WF)
   sums = prog.sums(raw, mask).numpy()
-  assert eng.calls == 3 and sums[-1] == 1.0
+  assert eng.calls == 1 + n_m and sums[-1] == 1.0
   v_nll, g_nll = O.nll_value_and_grad("constant", "matern52", model,
                                       g["dataset"], WFO)
   v_kl, g_kl = O.kl_value_and_grad("constant", "matern52", model, g["dataset"],
@@ -85,8 +89,19 @@ def test_combined_objective_program(monkeypatch):
   assert abs(sums[0] - (v_nll + 0.3 * v_kl)) < 1e-11 * abs(sums[0])
   want = H.grad_vec(g_nll, g["d"]) + 0.3 * H.grad_vec(g_kl, g["d"])
   assert H.rel(sums[1:-1], want) < 1e-10
+  # the round-1 decomposition (m + 2 weighted tasks sharing x) gives the same sums
+  monkeypatch.setattr(objectives, "KL_MULTI_RHS", False)
+  prog_w = objectives.compile_objective(objective, mean.constant, kernel.matern52,
+                                        dataset)
+  # nll launch + zero-mean kl launch + model-mean kl launch
+  assert len(prog_w.launches) == 3
+  assert H.rel(prog_w.sums(raw, mask).numpy(), sums) < 1e-11
   # zero mean: the model-mean tasks ride in the zero-mean launch
   g2, model2, params2, dataset2 = _case("kl_se_zero_d2")
+  prog2 = objectives.compile_objective(objectives.kl, mean.zero,
+                                       kernel.squared_exponential, dataset2)
+  assert len(prog2.launches) == 1
+  monkeypatch.setattr(objectives, "KL_MULTI_RHS", True)
   prog2 = objectives.compile_objective(objectives.kl, mean.zero,
                                        kernel.squared_exponential, dataset2)
   assert len(prog2.launches) == 1
