@@ -48,6 +48,9 @@ namespace hb {
                    const void*, double, double, int, double, int, int32_t*,     \
                    void*);                                                      \
   int fused_timeout_impl();                                                     \
+  int euclid_grad_impl(hb_handle_t, int, int, int, const int64_t*, int,         \
+                       const void*, int, const void*, const void*, const void*, \
+                       uint64_t, double, double, const void*, void*, void*);    \
   int nll_grad_mrhs_impl(hb_handle_t, int, int, int, const int64_t*, int,       \
                          const void*, int, const void*, const void*,            \
                          const int32_t*, const void*, uint64_t, const void*,    \
@@ -332,6 +335,15 @@ int hb_nll_grad_mrhs(hb_handle_t h, int kernel_id, int mean_id, int T,
   HB_DISPATCH(nll_grad_mrhs_impl, h, kernel_id, mean_id, T, offs, d, X, R, B,
               col_weight, col_mean, raw, warp_mask, task_weight, jitter, sums_out,
               info_out, stream);
+}
+
+int hb_euclid_grad(hb_handle_t h, int kernel_id, int mean_id, int T,
+                   const int64_t* offs, int d, const void* X, int R, const void* Yc,
+                   const void* mu0, const void* raw, uint64_t warp_mask,
+                   double mean_weight, double cov_weight, const void* task_weight,
+                   void* sums_out, void* stream) {
+  HB_DISPATCH(euclid_grad_impl, h, kernel_id, mean_id, T, offs, d, X, R, Yc, mu0, raw,
+              warp_mask, mean_weight, cov_weight, task_weight, sums_out, stream);
 }
 
 int hb_adam_step(hb_handle_t h, int P_, void* raw, void* m, void* v,

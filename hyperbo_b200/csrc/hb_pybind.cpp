@@ -125,6 +125,18 @@ PYBIND11_MODULE(_C, m) {
                          jitter, P(sums), (int32_t*)P(info), P(stream)),
                      "hb_nll_grad_mrhs");
            })
+      .def("euclid_grad",
+           [](Handle& s, int kernel_id, int mean_id, std::vector<int64_t> offs,
+              int d, ptr_t X, int R, ptr_t Yc, ptr_t mu0, ptr_t raw, uint64_t mask,
+              double mean_weight, double cov_weight, ptr_t weight, ptr_t sums,
+              ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_euclid_grad(s.h, kernel_id, mean_id, (int)offs.size() - 1,
+                                    offs.data(), d, P(X), R, P(Yc), P(mu0), P(raw),
+                                    mask, mean_weight, cov_weight, P(weight), P(sums),
+                                    P(stream)),
+                     "hb_euclid_grad");
+           })
       .def("adam_step",
            [](Handle& s, int np, ptr_t raw, ptr_t mm, ptr_t vv, ptr_t accepted,
               ptr_t sums, ptr_t scal, double lr, double b1, double b2, double eps,

@@ -289,6 +289,34 @@ class Engine:
         self._stream())
     return sums_out
 
+  def euclid_grad(self, kernel_id: int, mean_id: int, ds: PackedDataset, R: int,
+                  Yc: torch.Tensor, mu0: torch.Tensor, raw, mask: int,
+                  mean_weight: float = 1.0, cov_weight: float = 1.0,
+                  weights: Optional[torch.Tensor] = None,
+                  sums_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """hb_euclid_grad: sum_t w_t (mean_weight ||mu0 - m(x)|| + cov_weight
+    ||Yc Yc' - (K + nv I)||_F) and its raw-parameter gradient.  Yc: flat, task t
+    owns the (R, n_t) block at offs[t] * R (columns contiguous, already divided by
+    sqrt(m)); mu0: (sum n,)."""
+    raw = self.tensor(raw)
+    T = ds.num_tasks
+    if sums_out is None:
+      sums_out = torch.empty((3 + ds.d + 2,), device=self.device, dtype=self.dtype)
+    Yc = self.tensor(Yc).reshape(-1)
+    mu0 = self.tensor(mu0).reshape(-1)
+    if Yc.shape[0] != ds.offs[-1] * R or mu0.shape[0] != ds.offs[-1]:
+      raise ValueError("Yc / mu0 do not match the (tasks, R) layout")
+    if weights is not None:
+      weights = self.tensor(weights).reshape(-1)
+      if weights.shape[0] != T:
+        raise ValueError(f"weights has {weights.shape[0]} entries for {T} tasks")
+    self.h.euclid_grad(kernel_id, mean_id, ds.offs, ds.d, ds.x.data_ptr(), R,
+                       Yc.data_ptr(), mu0.data_ptr(), raw.data_ptr(), mask,
+                       float(mean_weight), float(cov_weight),
+                       weights.data_ptr() if weights is not None else 0,
+                       sums_out.data_ptr(), self._stream())
+    return sums_out
+
   def generation(self) -> int:
     """Bumped whenever a workspace buffer / cached plan of the handle moves:
     CUDA graphs that captured engine calls must be re-captured then."""

@@ -198,6 +198,16 @@ class _LaunchMRHS:
     self.jitter, self.scale = jitter, 1.0
 
 
+class _LaunchEuc:
+  """One hb_euclid_grad call: the Euclidean regulariser (utils.py:151-173) on the
+  aligned sub-datasets that have the same number of columns."""
+
+  def __init__(self, ds, mean_id, R, Yc, mu0, weights, mean_weight, cov_weight):
+    self.ds, self.mean_id, self.R, self.Yc, self.mu0 = ds, mean_id, R, Yc, mu0
+    self.weights, self.scale = weights, 1.0
+    self.mean_weight, self.cov_weight = mean_weight, cov_weight
+
+
 # False: the partial KL runs as m + 2 weighted NLL tasks that share x (the
 # round-1 decomposition, kept as a cross-check of the multi-RHS entry)
 KL_MULTI_RHS = True
@@ -228,7 +238,10 @@ class ObjectiveProgram:
       out = torch.empty(self.P + 2, device=eng.device, dtype=eng.dtype)
     out.zero_()
     for l in self.launches:
-      if isinstance(l, _LaunchMRHS):
+      if isinstance(l, _LaunchEuc):
+        s = eng.euclid_grad(self.kid, l.mean_id, l.ds, l.R, l.Yc, l.mu0, raw, mask,
+                            l.mean_weight, l.cov_weight, weights=l.weights)
+      elif isinstance(l, _LaunchMRHS):
         s = eng.nll_grad_mrhs(self.kid, l.mean_id, l.ds, l.R, l.B, l.col_w,
                               l.col_mean, raw, mask, weights=l.weights,
                               jitter=l.jitter)
@@ -381,9 +394,29 @@ def compile_objective(objective, mean_func, cov_func, dataset, rank=0, world=1
         trace_terms.append((c, eng.pack([(i, x, y) for i, (x, y, _) in
                                          enumerate(mine)]), eps))
     else:
-      raise NotImplementedError(
-          "the Euclidean regulariser (objectives.py:104-106) is value-only "
-          "here (GP.stats); it has no engine program / gradient")
+      # the Euclidean regulariser (objectives.py:104-106, utils.py:151-173):
+      # hb_euclid_grad, value and gradient, no factorisation
+      subs = _aligned_subs(dataset)
+      if not subs:
+        continue
+      c = coef / len(subs)
+      by_m = {}
+      for si, (_, x, y) in enumerate(subs):
+        if (rr + si) % world != rank:
+          continue
+        x, y = eng.tensor(x), eng.tensor(y)
+        m = y.shape[1]
+        d = d or int(x.shape[1])
+        mu0 = y.mean(dim=1)
+        by_m.setdefault(m, []).append((x, (y - mu0[:, None]) / math.sqrt(m), mu0))
+      rr += len(subs)
+      for m, mine in by_m.items():
+        ds = eng.pack([(i, x, mu0) for i, (x, _, mu0) in enumerate(mine)])
+        Yc = torch.cat([yc.T.reshape(-1) for _, yc, _ in mine]).contiguous()
+        wts = torch.full((len(mine),), c, device=eng.device, dtype=eng.dtype)
+        launches.append(_LaunchEuc(ds, mid, m, Yc, ds.y.reshape(-1), wts,
+                                   float(kw.get("mean_weight", 1.0)),
+                                   float(kw.get("cov_weight", 1.0))))
   # (const is added by every rank AFTER the all-reduce of the partial vectors)
   return ObjectiveProgram(eng, kid, d or 1, launches, const, world, trace_terms)
 
@@ -393,9 +426,11 @@ def multivariate_normal_divergence(mean_func, cov_func, params, dataset,
                                    distance=_utils.kl_multivariate_normal):
   """Divergence between N(sample mean, sample cov) of every ALIGNED sub-dataset
   and the GP's N(m(x), K(x,x) + noise I), averaged over those sub-datasets
-  (objectives.py:29-101).  The partial KL runs on the factorisation kernels;
-  the whitened KL (partial=False) and the Euclidean distance are value-only
-  diagnostics assembled from the engine's Gram matrix with cuSOLVER."""
+  (objectives.py:29-101).  The partial KL runs on the factorisation kernels
+  (hb_nll_grad_mrhs) and the Euclidean distance has its own program
+  (hb_euclid_grad, used by value_and_grad / training); this VALUE entry
+  assembles the whitened KL (partial=False) and the Euclidean distance from
+  the engine's Gram matrix with library calls, as GP.stats() diagnostics."""
   kind, kw = _utils.distance_spec(distance)
   eng = _engine.Engine.get()
   subs = _aligned_subs(dataset)

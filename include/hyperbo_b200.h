@@ -205,6 +205,23 @@ int hb_nll_grad_mrhs(hb_handle_t h, int kernel_id, int mean_id, int T,
                      double jitter, void* sums_out, int32_t* info_out_or_null,
                      void* stream);
 
+/* The reference's other regulariser on aligned data: the Euclidean distance of
+ * utils.euclidean_multivariate_normal (gp_utils/utils.py:151-173) inside
+ * objectives.multivariate_normal_divergence (gp_utils/objectives.py:29-101),
+ * value AND gradient (objectives.nll_regeuc*, objectives.py:218,238):
+ *   sums_out[0]   = sum_t w_t ( mean_weight ||mu0_t - m(x_t)||_2
+ *                             + cov_weight  ||Yc_t Yc_t' - (K_t + nv I)||_F ),
+ *   sums_out[1+p] = d sums_out[0] / d raw_p,   sums_out[1+P] = task count.
+ * Yc: per task the (R, n_t) block of centred columns ALREADY scaled by
+ * 1/sqrt(m) (so Yc Yc' = cov(y, bias=True)), same layout as B of
+ * hb_nll_grad_mrhs; mu0: (sum n) row means.  No factorisation: one pass over
+ * the lower-triangular 64x64 tiles evaluates K and dK from X. */
+int hb_euclid_grad(hb_handle_t h, int kernel_id, int mean_id, int T,
+                   const int64_t* offs_host, int d, const void* X, int R,
+                   const void* Yc, const void* mu0, const void* raw,
+                   uint64_t warp_mask, double mean_weight, double cov_weight,
+                   const void* task_weight_or_null, void* sums_out, void* stream);
+
 /* ---- a11: one optax.adam update (gp_utils/gp.py:124,143-144) ------------ */
 /* state (device, handle dtype): raw[P], m[P], v[P], accepted[P].
  * scalars_io (device, 4 scalars): [0] loss of this step (written),

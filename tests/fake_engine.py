@@ -136,6 +136,53 @@ class FakeEngine(_engine.Engine):
       res_t = sums_out
     return res_t
 
+  def euclid_grad(self, kernel_id, mean_id, ds, R, Yc, mu0, raw, mask,
+                  mean_weight=1.0, cov_weight=1.0, weights=None, sums_out=None):
+    """hb_euclid_grad contract, dense closed form (d ||E||_F = <E, dE> / ||E||_F)."""
+    raw = self._np(raw)
+    T, d = ds.num_tasks, ds.d
+    P = 3 + d
+    warped = np.array([(mask >> p) & 1 for p in range(P)], dtype=bool)
+    theta = np.where(warped, O.softplus(raw) + O.EPS_WARP, raw)
+    chain = np.where(warped, O.sigmoid(raw), 1.0)
+    c = theta[0] if mean_id == 1 else 0.0
+    sv, nv, ls = theta[1], theta[2], theta[3:]
+    name = _KERNELS[kernel_id]
+    Yc, mu0 = self._np(Yc).reshape(-1), self._np(mu0).reshape(-1)
+    w = np.ones(T) if weights is None else self._np(weights).reshape(T)
+    out = np.zeros(P + 2)
+    x = ds.x.numpy()
+    for t in range(T):
+      lo, hi = ds.offs[t], ds.offs[t + 1]
+      n = hi - lo
+      if n == 0:
+        continue
+      xt = x[lo:hi]
+      yc = Yc[lo * R:hi * R].reshape(R, n).T
+      r2, diff = O._scaled_sqdist(xt, xt, ls)  # pylint: disable=protected-access
+      k = O._kernel_from_r2(name, r2, sv)  # pylint: disable=protected-access
+      e = yc @ yc.T - k - nv * np.eye(n)
+      f = math.sqrt(float(np.sum(e * e)))
+      dm = mu0[lo:hi] - c
+      nm = math.sqrt(float(np.sum(dm * dm)))
+      out[0] += w[t] * (mean_weight * nm + cov_weight * f)
+      pw = O._pair_weight(name, r2, k, sv)  # pylint: disable=protected-access
+      grad = np.zeros(P)
+      if mean_id == 1 and nm > 0:
+        grad[0] = -mean_weight * float(np.sum(dm)) / nm
+      if f > 0:
+        grad[1] = -cov_weight * float(np.sum(e * k)) / sv / f
+        grad[2] = -cov_weight * float(np.trace(e)) / f
+        grad[3:] = -cov_weight * np.einsum("ij,ijk->k", e * pw, diff * diff) / ls / f
+      out[1:-1] += w[t] * grad * chain
+      out[-1] += 1.0
+    self.calls += 1
+    res_t = torch.from_numpy(out)
+    if sums_out is not None:
+      sums_out.copy_(res_t)
+      res_t = sums_out
+    return res_t
+
   # ---- the rest of the Engine surface (same contracts as engine.py) ---------
   @staticmethod
   def _np(a):

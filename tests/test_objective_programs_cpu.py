@@ -105,9 +105,63 @@ def test_combined_objective_program(monkeypatch):
   prog2 = objectives.compile_objective(objectives.kl, mean.zero,
                                        kernel.squared_exponential, dataset2)
   assert len(prog2.launches) == 1
-  with pytest.raises(NotImplementedError):
-    objectives.compile_objective(objectives.euc, mean.constant, kernel.matern52,
-                                 dataset)
+
+
+def _fd_grad(fn, model, d, h=1e-6):
+  """central differences of fn(model) over the raw parameters (order of raw_vec)."""
+  out = []
+  for key, idx in ([("constant", None), ("signal_variance", None),
+                    ("noise_variance", None)] + [("lengthscale", k) for k in range(d)]):
+    vals = []
+    if key not in model:
+      out.append(0.0)
+      continue
+    for sgn in (1.0, -1.0):
+      m = {k: np.array(v, dtype=np.float64, copy=True) for k, v in model.items()}
+      if idx is None:
+        m[key] = m[key] + sgn * h
+      else:
+        m[key][idx] += sgn * h
+      vals.append(fn(m))
+    out.append((vals[0] - vals[1]) / (2 * h))
+  return np.array(out)
+
+
+@pytest.mark.parametrize("name", H.golden_cases(kl=True))
+def test_euclidean_regulariser_program(monkeypatch, name):
+  """objectives.euc / nll_regeuc(c) as engine programs (hb_euclid_grad): the value
+  is the committed fixture, the gradient matches central differences of the
+  oracle's restatement of utils.euclidean_multivariate_normal."""
+  fake_engine.install(monkeypatch)
+  g, model, params, dataset = _case(name)
+  mf, cf = MEANS[g["mean"]], COVS[g["cov"]]
+  d = g["d"]
+  val, grads = objectives.value_and_grad(objectives.euc, mf, cf, params, dataset, WF)
+  assert abs(float(val) - g["euc"]) < 1e-11 * abs(g["euc"])
+  model_full = dict(model)
+  model_full["lengthscale"] = np.broadcast_to(
+      np.asarray(model["lengthscale"], dtype=np.float64), (d,)).copy()
+  fd = _fd_grad(lambda m: O.multivariate_normal_divergence(
+      g["mean"], g["cov"], m, g["dataset"], WFO,
+      distance=O.euclidean_multivariate_normal), model_full, d)
+  got = H.grad_vec(grads, d)
+  if g["mean"] == "zero":
+    fd[0] = 0.0
+  assert H.rel(got, fd) < 1e-6
+  # weights of the two norms + the nll_regeuc(c) combination
+  import functools
+  dist = functools.partial(utils.euclidean_multivariate_normal, mean_weight=0.5,
+                           cov_weight=2.0)
+  objective = objectives.add(objectives.nll, objectives.mul(
+      0.3, functools.partial(objectives.multivariate_normal_divergence,
+                             distance=dist)))
+  v2, _ = objectives.value_and_grad(objective, mf, cf, params, dataset, WF)
+  want = O.neg_log_marginal_likelihood(g["mean"], g["cov"], model, g["dataset"], WFO) \
+      + 0.3 * O.multivariate_normal_divergence(
+          g["mean"], g["cov"], model, g["dataset"], WFO,
+          distance=functools.partial(O.euclidean_multivariate_normal,
+                                     mean_weight=0.5, cov_weight=2.0))
+  assert abs(float(v2) - want) < 1e-10 * abs(want)
 
 
 def test_multi_column_nll_value(monkeypatch):
