@@ -48,6 +48,9 @@ namespace hb {
                    const void*, double, double, int, double, int, int32_t*,     \
                    void*);                                                      \
   int fused_timeout_impl();                                                     \
+  int predict_cov_impl(hb_handle_t, int, int, int64_t, int, const void*,        \
+                       const void*, const void*, uint64_t, int64_t, const void*,\
+                       double, double, void*, void*, void*);                    \
   int euclid_grad_impl(hb_handle_t, int, int, int, const int64_t*, int,         \
                        const void*, int, const void*, const void*, const void*, \
                        uint64_t, double, double, const void*, void*, void*);    \
@@ -142,7 +145,7 @@ int hb_destroy(hb_handle_t h) {
                 &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                 &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
                 &h->vpart, &h->pcache, &h->pre, &h->sync, &h->apart,
-                &h->mrz,   &h->mra,    &h->zeros};
+                &h->mrz,   &h->mra,    &h->zeros, &h->vt};
   for (auto* b : all)
     if (b->p) cudaFree(b->p);
   for (auto& p : h->plans) {
@@ -379,6 +382,15 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
   HB_DISPATCH(predict_impl, h, kernel_id, mean_id, n, d, X, cache, raw,
               warp_mask, nq, Xq, noise_add_flag, var_scale, acq_id, acq_param,
               mu_out, var_out, acq_out, stream);
+}
+
+int hb_predict_cov(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
+                   const void* X, const void* cache, const void* raw,
+                   uint64_t warp_mask, int64_t nq, const void* Xq,
+                   double noise_add_flag, double var_scale, void* mu_out,
+                   void* cov_out, void* stream) {
+  HB_DISPATCH(predict_cov_impl, h, kernel_id, mean_id, n, d, X, cache, raw, warp_mask,
+              nq, Xq, noise_add_flag, var_scale, mu_out, cov_out, stream);
 }
 
 int hb_nll_grad_multi(hb_handle_t h, int kernel_id, int mean_id, int S, int T,

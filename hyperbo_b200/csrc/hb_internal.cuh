@@ -58,10 +58,11 @@ struct hb_handle_s {
   uint64_t clock = 0;
   hb::host::Plan plans[hb::host::NPLAN];
   hb::host::Buf theta, Lt, Mt, Wt, zz, z, alpha, logdet, asum, nll_task, gpart, gtask, info, bad,
-      sums, kst, mupart, vpart, pcache, stamps, pre, sync, apart, mrz, mra, zeros;
+      sums, kst, mupart, vpart, pcache, stamps, pre, sync, apart, mrz, mra, zeros, vt;
   bool attr_set = false;
   bool bo_attr_set = false;
   bool mrhs_attr_set = false;
+  bool cov_attr_set = false;
   int sm_count = 0;
   int fused = 1;               // HB_FUSED env: 0 = launch-per-column path, 2 = always persistent
   int fused_grid = 0;          // HB_FUSED_GRID env: CTAs of the persistent kernel
@@ -119,7 +120,7 @@ inline size_t total_ws(hb_handle_t h) {
                       &h->logdet, &h->asum, &h->nll_task, &h->gpart, &h->gtask,
                       &h->info,  &h->bad,   &h->sums,  &h->kst,  &h->mupart,
                       &h->vpart, &h->pcache, &h->pre, &h->sync, &h->apart,
-                      &h->mrz,   &h->mra,    &h->zeros};
+                      &h->mrz,   &h->mra,    &h->zeros, &h->vt};
   size_t s = 0;
   for (auto* b : all) s += b->cap;
   for (auto& p : h->plans) {

@@ -261,6 +261,16 @@ PYBIND11_MODULE(_C, m) {
                                 P(stream)),
                      "hb_predict");
            })
+      .def("predict_cov",
+           [](Handle& s, int kernel_id, int mean_id, int64_t n, int d, ptr_t X,
+              ptr_t cache, ptr_t raw, uint64_t mask, int64_t nq, ptr_t Xq,
+              double noise_flag, double var_scale, ptr_t mu, ptr_t cov, ptr_t stream) {
+             py::gil_scoped_release rel;
+             s.check(hb_predict_cov(s.h, kernel_id, mean_id, n, d, P(X), P(cache),
+                                    P(raw), mask, nq, P(Xq), noise_flag, var_scale,
+                                    P(mu), P(cov), P(stream)),
+                     "hb_predict_cov");
+           })
       .def("acquisition",
            [](Handle& s, int acq_id, double param, int64_t nq, ptr_t mu, ptr_t var,
               ptr_t out, ptr_t stream) {

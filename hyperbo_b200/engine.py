@@ -457,6 +457,26 @@ class Engine:
                    acq.data_ptr() if acq_id else 0, self._stream())
     return mu, var, acq
 
+  def predict_cov(self, kernel_id: int, mean_id: int, x, cache, raw, mask: int, xq,
+                  noise_flag=0.0, var_scale=1.0):
+    """hb_predict_cov: (mu (nq,1), cov (nq,nq)) of gp.predict(full_cov=True),
+    cov = (k(xq,xq) - V'V + noise_flag * noise_variance * I) * var_scale."""
+    xq = self.tensor(xq)
+    nq, d = xq.shape
+    self._check_dim(d)
+    raw = self.tensor(raw)
+    if x is None or x.shape[0] == 0:
+      n, xp, cp = 0, 0, 0
+    else:
+      x = self.tensor(x)
+      n, xp, cp = x.shape[0], x.data_ptr(), cache.data_ptr()
+    mu = torch.empty((nq, 1), device=self.device, dtype=self.dtype)
+    cov = torch.empty((nq, nq), device=self.device, dtype=self.dtype)
+    self.h.predict_cov(kernel_id, mean_id, n, d, xp, cp, raw.data_ptr(), mask, nq,
+                       xq.data_ptr(), float(noise_flag), float(var_scale),
+                       mu.data_ptr(), cov.data_ptr(), self._stream())
+    return mu, cov
+
   def acquisition(self, acq_id: int, param: float, mu, var) -> torch.Tensor:
     mu = self.tensor(mu).reshape(-1)
     var = self.tensor(var).reshape(-1)

@@ -538,29 +538,25 @@ def predict(mean_func,
   if x_observed is None or torch.as_tensor(x_observed).shape[0] == 0:
     # prior (gp.py:275-282)
     if full_cov:
-      mu = mean_func(params, x_query, warp_func=warp_func).to(eng.device)
-      return mu, cov_func(params, x_query, warp_func=warp_func)
+      return eng.predict_cov(kid, mid, None, None, raw, mask, x_query,
+                             noise_flag=_noise_flag, var_scale=_var_scale)
     mu, var, _ = eng.predict(kid, mid, None, None, raw, mask, x_query,
                              noise_flag=_noise_flag, var_scale=_var_scale)
     return mu, var
   x_observed = eng.tensor(x_observed)
   packed = getattr(cache, "packed", None) if cache is not None else None
   if packed is None:
-    chol, kinvy, _, packed = linalg.solve_gp_linear_system(
+    _, _, _, packed = linalg.solve_gp_linear_system(
         mean_func, cov_func, params, x_observed, y_observed, warp_func,
         return_cache=True)
-  else:
-    chol, kinvy = cache.chol, cache.kinvy
   if not full_cov:
     mu, var, _ = eng.predict(kid, mid, x_observed, packed, raw, mask, x_query,
                              noise_flag=_noise_flag, var_scale=_var_scale)
     return mu, var
-  # full covariance (gp.py:295-300): off the hot path, library triangular solve
-  cov = cov_func(params, x_observed, x_query, warp_func=warp_func)
-  mu = cov.T @ kinvy + mean_func(params, x_query, warp_func=warp_func).to(
-      eng.device)
-  v = torch.linalg.solve_triangular(chol, cov, upper=False)
-  return mu, cov_func(params, x_query, warp_func=warp_func) - v.T @ v
+  # full covariance (gp.py:295-300): V = L^-1 K* and K** - V'V on the tensor pipe
+  # (hb_predict_cov), noise / N/(N-1) of GP.predict fused into the epilogue
+  return eng.predict_cov(kid, mid, x_observed, packed, raw, mask, x_query,
+                         noise_flag=_noise_flag, var_scale=_var_scale)
 
 
 class GP:
@@ -761,19 +757,9 @@ class GP:
       cache = self.params.cache.get(sub_dataset_key) if has_obs else None
     else:
       x_obs = y_obs = cache = None
-    if not full_cov:
-      return predict(self.mean_func, self.cov_func, self.params, x_obs, y_obs,
-                     queried_inputs, self.warp_func, False, cache,
-                     _noise_flag=noise_flag, _var_scale=scale)
-    mu, cov = predict(self.mean_func, self.cov_func, self.params, x_obs, y_obs,
-                      queried_inputs, self.warp_func, True, cache)
-    if with_noise:
-      noise_variance, = retrieve_params(self.params, ["noise_variance"],
-                                        warp_func=self.warp_func)
-      nv = float(torch.as_tensor(noise_variance, dtype=torch.float64).reshape(-1)[0])
-      cov = cov + torch.eye(cov.shape[0], device=cov.device,
-                            dtype=cov.dtype) * nv
-    return mu, cov * scale
+    return predict(self.mean_func, self.cov_func, self.params, x_obs, y_obs,
+                   queried_inputs, self.warp_func, full_cov, cache,
+                   _noise_flag=noise_flag, _var_scale=scale)
 
   def engine_ids(self, d: int):
     """(kernel_id, mean_id, raw, warp_mask) of this model for the C ABI."""

@@ -289,6 +289,17 @@ int hb_predict(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
                double noise_add_flag, double var_scale, int acq_id,
                double acq_param, void* mu_out, void* var_out, void* acq_out,
                void* stream);
+/* gp.predict(..., full_cov=True) (gp_utils/gp.py:295-300) with GP.predict's noise
+ * and N/(N-1) handling (gp.py:607-619):
+ *   cov = (k(Xq, Xq) - (L^{-1} K*)' (L^{-1} K*) + noise_add I) * var_scale
+ * cov_out: (nq, nq) row-major, both triangles; mu_out (nq,) may be NULL.
+ * nq <= 16384 (one pass; HB_ERR_UNSUPPORTED beyond).  n = 0: the prior. */
+int hb_predict_cov(hb_handle_t h, int kernel_id, int mean_id, int64_t n, int d,
+                   const void* X, const void* cache, const void* raw,
+                   uint64_t warp_mask, int64_t nq, const void* Xq,
+                   double noise_add_flag, double var_scale, void* mu_out_or_null,
+                   void* cov_out, void* stream);
+
 /* acfun_sub alone on given mu / var vectors (bo_utils/acfun.py:96-142). */
 int hb_acquisition(hb_handle_t h, int acq_id, double acq_param, int64_t nq,
                    const void* mu, const void* var, void* out, void* stream);

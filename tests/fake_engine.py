@@ -275,6 +275,21 @@ class FakeEngine(_engine.Engine):
     return (torch.from_numpy(mu) if want_mu else None,
             torch.from_numpy(var) if want_var else None, acq)
 
+  def predict_cov(self, kernel_id, mean_id, x, cache, raw, mask, xq, noise_flag=0.0,
+                  var_scale=1.0):
+    xq = self._np(xq)
+    theta = self._theta(raw, mask, xq.shape[1])
+    mu = np.full((xq.shape[0], 1), theta[0] if mean_id == 1 else 0.0)
+    cov = self._gram(kernel_id, xq, xq, theta)
+    if x is not None and torch.as_tensor(x).shape[0] > 0:
+      chol, alpha = cache
+      ks = self._gram(kernel_id, self._np(x), xq, theta)
+      mu = mu + ks.T @ alpha
+      v = spla.solve_triangular(chol, ks, lower=True)
+      cov = cov - v.T @ v
+    cov = (cov + noise_flag * theta[2] * np.eye(xq.shape[0])) * var_scale
+    return torch.from_numpy(mu), torch.from_numpy(cov)
+
   def acquisition(self, acq_id, param, mu, var):
     mu, var = self._np(mu).reshape(-1, 1), self._np(var).reshape(-1, 1)
     return torch.from_numpy(self._acq(acq_id, float(param), mu, var))
