@@ -202,6 +202,14 @@ int hb_debug_fused_timeout(hb_handle_t h) {
 }
 
 #ifdef HB_STAMPS
+extern "C++" {
+namespace hb { namespace f64 { int dbg_potrf64_impl(int, int, long long*); }
+               namespace f32 { int dbg_potrf64_impl(int, int, long long*); } }
+}
+int hb_debug_potrf64(int f32, int grid, int reps, long long* host_out) {
+  return f32 ? hb::f32::dbg_potrf64_impl(grid, reps, host_out)
+             : hb::f64::dbg_potrf64_impl(grid, reps, host_out);
+}
 int hb_debug_stamps(hb_handle_t h, long long* host_out, int64_t n) {
   cudaDeviceSynchronize();
   return cudaMemcpy(host_out, h->stamps.p, n * 8, cudaMemcpyDeviceToHost);
