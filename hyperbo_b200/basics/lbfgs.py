@@ -15,6 +15,57 @@ from typing import Callable, List, Optional, Tuple
 import numpy as np
 
 ValGrad = Callable[[np.ndarray], Tuple[float, np.ndarray]]
+MultiValGrad = Callable[[List[np.ndarray]], List[Tuple[float, np.ndarray]]]
+
+
+class _Evaluator:
+  """The objective behind a small memo of recent points.
+
+  * The driver re-evaluates the point its line search just accepted
+    (lbfgs.py:301 after :136): same bytes, same deterministic engine call, so the
+    memo returns the stored pair instead of a second factorisation pass.
+  * With `multi_fn` (S points in ONE engine call, hb_nll_grad_multi) the line
+    search evaluates a trial step together with its two possible successors
+    (alpha * tau, alpha * 2.1) from the second trial on: the next trial is then
+    already known and a long search needs half the device round trips.  The sequence of trial
+    steps and every decision are those of the plain search.
+  """
+
+  def __init__(self, fn: ValGrad, multi_fn: Optional[MultiValGrad] = None,
+               keep: int = 16):
+    self.fn, self.multi_fn, self.keep = fn, multi_fn, keep
+    self.memo = {}
+    self.calls = 0        # engine round trips
+    self.points = 0       # points evaluated (speculative ones included)
+
+  def _store(self, x, res):
+    self.memo[x.tobytes()] = res
+    while len(self.memo) > self.keep:
+      self.memo.pop(next(iter(self.memo)))
+
+  def __call__(self, x: np.ndarray):
+    hit = self.memo.get(x.tobytes())
+    if hit is not None:
+      return hit
+    res = self.fn(x)
+    self.calls += 1
+    self.points += 1
+    self._store(x, res)
+    return res
+
+  def prefetch(self, xs: List[np.ndarray]):
+    """xs[0] is the next trial, the rest its possible successors: if the trial is
+    not known yet, evaluate all unknown points in one call."""
+    if self.multi_fn is None or xs[0].tobytes() in self.memo:
+      return
+    todo = [x for x in xs if x.tobytes() not in self.memo]
+    if len(todo) < 2:
+      return
+    out = self.multi_fn(todo)
+    self.calls += 1
+    self.points += len(todo)
+    for x, res in zip(todo, out):
+      self._store(x, res)
 
 
 def backtracking_linesearch(val_and_grad_fn: ValGrad, cur_val: float,
@@ -30,7 +81,12 @@ def backtracking_linesearch(val_and_grad_fn: ValGrad, cur_val: float,
     logging.info("Incorrect descent direction %f. Exiting linesearch", slope)
     return cur_val, 0.0
   new_val = cur_val
-  for _ in range(max_steps):
+  prefetch = getattr(val_and_grad_fn, "prefetch", None)
+  for trial in range(max_steps):
+    # (the first trial is accepted most of the time: speculate only once it was
+    # not) this trial + both possible next trials in one call
+    if prefetch is not None and trial > 0:
+      prefetch([x + a * direction for a in (alpha, alpha * tau, alpha * 2.1)])
     new_val, new_grads = val_and_grad_fn(x + alpha * direction)
     armijo = math.isfinite(new_val) and cur_val + alpha * c1 * slope >= new_val
     if armijo:
@@ -64,9 +120,24 @@ def descent_direction(grads: np.ndarray, s: List[np.ndarray],
 def lbfgs(val_and_grad_fn: ValGrad, x0: np.ndarray, memory: int = 10,
           ls_steps: int = 50, steps: int = 100, alpha: float = 1.0,
           tol: float = 1e-6, ls_tau: float = 0.5, state=None,
-          callback: Optional[Callable] = None):
+          callback: Optional[Callable] = None,
+          multi_fn: Optional[MultiValGrad] = None, stats: Optional[dict] = None):
   """Minimise with L-BFGS.  Returns (value, x, state) like lbfgs.py:186-349;
-  `state = (s, y, old_grads, old_x)` resumes the Hessian estimate."""
+  `state = (s, y, old_grads, old_x)` resumes the Hessian estimate.  `multi_fn`
+  (several points per engine call) enables the speculative line search of
+  _Evaluator; `stats` receives the number of engine calls / points."""
+  val_and_grad_fn = _Evaluator(val_and_grad_fn, multi_fn)
+  try:
+    return _lbfgs(val_and_grad_fn, x0, memory, ls_steps, steps, alpha, tol, ls_tau,
+                  state, callback)
+  finally:
+    if stats is not None:
+      stats["calls"] = val_and_grad_fn.calls
+      stats["points"] = val_and_grad_fn.points
+
+
+def _lbfgs(val_and_grad_fn, x0, memory, ls_steps, steps, alpha, tol, ls_tau, state,
+           callback):
   x = np.array(x0, dtype=np.float64)
   if state is None:
     s_k: List[np.ndarray] = []

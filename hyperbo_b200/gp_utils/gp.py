@@ -336,10 +336,39 @@ def _infer_parameters_quasi_newton(eng, kid, mid, params, dataset, warp_func,
       callback(step, params_utils.unpack_like(template, to_raw(model_params), d,
                                               need_mean), loss)
 
+  def val_and_grad_multi(vs):
+    """Several points in ONE engine call (hb_nll_grad_multi, the second batch
+    axis): the speculative line search of basics/lbfgs.py."""
+    raws = np.stack([to_raw(v) for v in vs])
+    s = eng.nll_grad_multi(kid, mid, ds, raws, mask).cpu().numpy()
+    out = []
+    for row in s:
+      cnt = max(row[-1], 1.0)
+      out.append((float(row[0] / cnt), from_raw_grad(row[1:-1] / cnt)))
+    return out
+
+  # speculation pays while three parameter sets still fit the GPU in one wave of
+  # the persistent kernel (small / few tasks: the notebook-scale case, where a
+  # call is latency-bound); bigger batches keep the plain sequential search
+  multi = None
+  if (method == "lbfgs" and world == 1 and
+      not isinstance(ds, obj.ObjectiveProgram) and
+      getattr(eng, "h", None) is not None and
+      os.environ.get("HB_LBFGS_SPECULATE", "1") != "0"):
+    tiles = sum(((ds.offs[t + 1] - ds.offs[t] + 63) // 64) *
+                ((ds.offs[t + 1] - ds.offs[t] + 63) // 64 + 1) // 2
+                for t in range(ds.num_tasks))
+    if 0 < 3 * tiles <= 444:
+      multi = val_and_grad_multi
+
   if method == "lbfgs":
+    ls_stats = {}
     _, v, _ = _lbfgs.lbfgs(val_and_grad, v0,
                            steps=params.config["max_training_step"],
-                           alpha=params.config.get("alpha", 1.0), callback=cb)
+                           alpha=params.config.get("alpha", 1.0), callback=cb,
+                           multi_fn=multi, stats=ls_stats)
+    logging.info("lbfgs: %s engine calls for %s points", ls_stats.get("calls"),
+                 ls_stats.get("points"))
   else:
     v, _ = _bfgs.bfgs(val_and_grad, v0, tol=params.config["tol"],
                       max_training_step=params.config["max_training_step"])

@@ -180,3 +180,37 @@ def test_simulated_bo_picks_the_oracle_argmax():
                          O.DEFAULT_WARP_FUNC)
   assert out.x.shape == (61, d)
   assert np.allclose(out.x[-1].cpu().numpy(), xq[int(np.argmax(ei_ref))])
+
+
+def test_lbfgs_memo_and_speculative_line_search_keep_the_trajectory():
+  """The evaluator behind the driver (basics/lbfgs.py::_Evaluator): the re-evaluation
+  of an accepted point is served from the memo, and with a multi-point objective
+  the line search needs about half the engine round trips -- same iterates."""
+  calls = {"single": 0, "multi": 0}
+
+  def fn(x):
+    calls["single"] += 1
+    return rosen(x)
+
+  def multi(xs):
+    calls["multi"] += 1
+    return [rosen(x) for x in xs]
+
+  x0 = np.array([-1.2, 1.0])
+  ref_calls = {"n": 0}
+
+  def fn_ref(x):
+    ref_calls["n"] += 1
+    return rosen(x)
+
+  # reference trajectory: the plain driver without memo (private entry)
+  v_ref, x_ref, _ = lbfgs._lbfgs(fn_ref, x0, 10, 50, 60, 1.0, 1e-16, 0.5, None, None)
+  st_a, st_b = {}, {}
+  v_a, x_a, _ = lbfgs.lbfgs(fn, x0, steps=60, tol=1e-16, stats=st_a)
+  n_single = calls["single"]
+  v_b, x_b, _ = lbfgs.lbfgs(fn, x0, steps=60, tol=1e-16, multi_fn=multi, stats=st_b)
+  assert np.array_equal(x_a, x_ref) and v_a == v_ref     # memo: identical iterates
+  assert np.array_equal(x_b, x_ref) and v_b == v_ref     # speculation: identical too
+  assert st_a["calls"] == n_single < ref_calls["n"]      # accepted points not re-run
+  assert st_b["calls"] < st_a["calls"]                   # fewer round trips
+  assert st_b["points"] >= st_a["points"]                # (some speculated points unused)
