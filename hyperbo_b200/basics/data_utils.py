@@ -1,11 +1,37 @@
-"""Per-step sub-sampling -- mirrors hyperbo/basics/data_utils.py:72-100."""
+"""Per-step sub-sampling and dataset logging -- mirrors
+hyperbo/basics/data_utils.py:29-100."""
 from __future__ import annotations
 
+import logging
+
+import numpy as np
 import torch
 
 from hyperbo_b200.basics import definitions as defs
 
 SubDataset = defs.SubDataset
+
+
+def log_dataset(dataset):
+  """Log size, shapes and per-column mean / median / min / max of every
+  sub-dataset (data_utils.py:29-69; called by GP.train and the data loaders).
+  Empty arrays are reported as nan, non-array fields (aligned) as they are."""
+
+  def stat(f, a):
+    if not isinstance(a, (np.ndarray, torch.Tensor)):
+      return a
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return float("nan") if a.shape[0] == 0 else f(a)
+
+  logging.info(msg=f"dataset len = {len(dataset)}.")
+  for name, f in (("shape", np.shape),
+                  ("mean", lambda a: np.mean(a, axis=0)),
+                  ("median", lambda a: np.median(a, axis=0)),
+                  ("min", lambda a: np.min(a, axis=0)),
+                  ("max", lambda a: np.max(a, axis=0))):
+    summary = {k: tuple(stat(f, field) for field in tuple(s))
+               for k, s in dataset.items()}
+    logging.info(msg=f"dataset {name}: {summary}")
 
 
 def sub_sample_dataset_iterator(key, dataset, batch_size):

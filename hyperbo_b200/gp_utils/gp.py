@@ -620,6 +620,8 @@ class GP:
     ones(d) * l -- that is how ARD is switched on."""
     if not self.dataset:
       raise ValueError("Cannot initialize GPParams without dataset.")
+    if logging.getLogger().isEnabledFor(logging.INFO):  # gp.py:352
+      data_utils.log_dataset(self.dataset)
     if isinstance(self.params.config["objective"], str):
       self.params.config["objective"] = getattr(
           obj, self.params.config["objective"])

@@ -229,7 +229,7 @@ def test_api_surface_of_the_hot_path_modules():
                         "inverse_spdmatrix_vector_product", "svd_matrix_sqrt",
                         "safe_l2norm"],
       "basics.params_utils": ["retrieve_params"],
-      "basics.data_utils": ["sub_sample_dataset_iterator"],
+      "basics.data_utils": ["sub_sample_dataset_iterator", "log_dataset"],
       "basics.definitions": ["GPCache", "SubDataset", "GPParams"],
       "basics.lbfgs": ["lbfgs"],
       "basics.bfgs": ["bfgs"],
