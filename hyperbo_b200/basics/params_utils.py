@@ -1,8 +1,12 @@
-"""Parameter retrieval -- mirrors hyperbo/basics/params_utils.py:90-111, plus the
-model-dict <-> raw-vector packing of the C ABI (include/hyperbo_b200.h)."""
+"""Parameter retrieval, saving / loading and logging -- mirrors
+hyperbo/basics/params_utils.py:33-111,193-207, plus the model-dict <-> raw-vector
+packing of the C ABI (include/hyperbo_b200.h)."""
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, List, Optional, Tuple
+import logging
+import os
+import pickle
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -31,6 +35,76 @@ def retrieve_params(params: GPParams, keys: List[str],
     return [warp_func[k](model_params[k]) if k in warp_func else model_params[k]
             for k in keys]
   return [model_params[k] for k in keys]
+
+
+# ------------------------------------------------ checkpoints (host only) ---
+FINAL_PARAM_FILE_INFO = "FINAL"
+
+
+def _portable(tree):
+  """Callables -> their str (params_utils.py:78-80); device tensors -> numpy, so a
+  file written on a GPU box loads anywhere."""
+  if isinstance(tree, dict):
+    return {k: _portable(v) for k, v in tree.items()}
+  if isinstance(tree, (list, tuple)):
+    return type(tree)(_portable(v) for v in tree)
+  if isinstance(tree, torch.Tensor):
+    return tree.detach().cpu().numpy()
+  return str(tree) if callable(tree) else tree
+
+
+def save_to_file(filenm: str, state: Any = None):
+  """params_utils.py:45-53 (plain files instead of gfile)."""
+  if not state:
+    return
+  dirnm = os.path.dirname(filenm)
+  if dirnm and not os.path.exists(dirnm):
+    os.makedirs(dirnm, exist_ok=True)
+  with open(filenm, "wb") as f:
+    pickle.dump(state, f)
+
+
+def load_from_file(filenm: str):
+  """params_utils.py:56-61."""
+  if not os.path.exists(filenm):
+    raise FileNotFoundError(f"{filenm} does not exist.")
+  with open(filenm, "rb") as f:
+    return pickle.load(f)
+
+
+def save_params(filenm: str, params: Union[GPParams, Dict[str, Any]],
+                state: Any = None):
+  """params_utils.py:64-73: (params as a dict, state) pickled; the GPCache
+  entries (device factors) are not part of a checkpoint."""
+  if not isinstance(params, dict):
+    params = dict(params.__dict__)
+  params = dict(params)
+  params["cache"] = {}
+  save_to_file(filenm, (_portable(params), _portable(state) if state else state))
+
+
+def load_params(filenm: str, use_gpparams: bool = True,
+                include_state: bool = False):
+  """params_utils.py:76-87."""
+  params_dict, state = load_from_file(filenm)
+  params = GPParams(**params_dict) if use_gpparams else params_dict
+  if include_state:
+    return params, state
+  return params
+
+
+def log_params_loss(step: int, params: GPParams, loss: float,
+                    warp_func: Optional[Dict[str, Callable[[Any], Any]]] = None,
+                    params_save_file: Optional[str] = None):
+  """Log (and optionally checkpoint) the parameters and the loss
+  (params_utils.py:193-207)."""
+  keys = list(params.model.keys())
+  retrieved = dict(zip(keys, retrieve_params(params, keys, warp_func=warp_func)))
+  logging.info(msg=f"logging iter={step}, loss={loss}, "
+               f"params.model after warping={retrieved}")
+  if params_save_file is not None:
+    logging.info(msg=f"Saving params to {params_save_file}.")
+    save_params(params_save_file, params, state=(step, loss))
 
 
 # ---------------------------------------------------------------- packing ---

@@ -286,7 +286,7 @@ def shard_tasks(items: List, rank: int, world: int) -> List:
 
 def _infer_parameters_quasi_newton(eng, kid, mid, params, dataset, warp_func,
                                    method, key, batch_size, pack, callback,
-                                   world):
+                                   world, get_params_path=lambda x=0: None):
   """L-BFGS / BFGS branches of infer_parameters (gp.py:158-191): ONE
   sub-sampled batch (gp.py:102-107), then a host-side quasi-Newton driver whose
   objective is the engine's batched value-and-gradient."""
@@ -363,16 +363,21 @@ def _infer_parameters_quasi_newton(eng, kid, mid, params, dataset, warp_func,
 
   if method == "lbfgs":
     ls_stats = {}
-    _, v, _ = _lbfgs.lbfgs(val_and_grad, v0,
-                           steps=params.config["max_training_step"],
-                           alpha=params.config.get("alpha", 1.0), callback=cb,
-                           multi_fn=multi, stats=ls_stats)
+    final_loss, v, _ = _lbfgs.lbfgs(
+        val_and_grad, v0, steps=params.config["max_training_step"],
+        alpha=params.config.get("alpha", 1.0), callback=cb, multi_fn=multi,
+        stats=ls_stats)
     logging.info("lbfgs: %s engine calls for %s points", ls_stats.get("calls"),
                  ls_stats.get("points"))
   else:
     v, _ = _bfgs.bfgs(val_and_grad, v0, tol=params.config["tol"],
                       max_training_step=params.config["max_training_step"])
   params.model = params_utils.unpack_like(template, to_raw(v), d, need_mean)
+  if method == "lbfgs":  # gp.py:186-191 (the bfgs branch does not log / save)
+    params_utils.log_params_loss(step=params.config["max_training_step"],
+                                 params=params, loss=final_loss,
+                                 warp_func=warp_func,
+                                 params_save_file=get_params_path())
   params.cache = {}
   return params
 
@@ -393,8 +398,8 @@ def infer_parameters(mean_func,
   sums are combined with one all-reduce per step, so all ranks return identical
   parameters.
   """
-  if get_params_path is not None and get_params_path() is not None:
-    raise NotImplementedError("saving params to a path (params_utils.py:45-87)")
+  if not get_params_path:
+    get_params_path = lambda x=0: None  # gp.py:90-91
   if key is None:
     key = 0
     logging.info("Using default random state in infer_parameters.")
@@ -435,7 +440,7 @@ def infer_parameters(mean_func,
   if method != "adam":
     return _infer_parameters_quasi_newton(
         eng, kid, mid, params, dataset, warp_func, method, key, batch_size,
-        pack, callback, world)
+        pack, callback, world, get_params_path)
   needs_subsample = any(
       torch.as_tensor(s.x).shape[0] >= batch_size for s in dataset.values())
   dataset_iter = data_utils.sub_sample_dataset_iterator(key, dataset,
@@ -508,9 +513,16 @@ def infer_parameters(mean_func,
           dist.all_reduce(sums, op=dist.ReduceOp.SUM)
       else:
         sums = ds.sums(trainer.raw, mask)
-      if math.isfinite(float(sums[0] / sums[-1])):
+      final_loss = float(sums[0] / sums[-1])
+      if math.isfinite(final_loss):
         final = trainer.raw
+    else:
+      final_loss = float("nan")
     params.model = to_model(final)
+    # gp.py:151-157: log (and checkpoint, if a path is given) the final state
+    params_utils.log_params_loss(step=max_training_step, params=params,
+                                 loss=final_loss, warp_func=warp_func,
+                                 params_save_file=get_params_path())
   params.cache = {}
   return params
 

@@ -378,3 +378,26 @@ def test_sample_from_gp_uses_the_engine_factor():
   want = 5.0 + _np(torch.linalg.cholesky(cov)) @ z.numpy()
   assert got.shape == (150, 4)
   assert np.max(np.abs(got - want)) < 1e-9 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("method", ["adam", "lbfgs"])
+def test_train_writes_a_checkpoint(tmp_path, method):
+  """GP.train(get_params_path=...) (gp.py:151-157,186-191): the final parameters,
+  step and loss are pickled; load_params restores them."""
+  from hyperbo_b200.basics import params_utils
+  ds = {t: defs.SubDataset(*O.make_task(t, 30, 2, "matern32")) for t in range(3)}
+  params = defs.GPParams(
+      model=dict(O.init_raw_params(2)),
+      config={"method": method, "learning_rate": 1e-2, "max_training_step": 5,
+              "batch_size": 100, "alpha": 1.0})
+  model = gp.GP(dataset=ds, mean_func=mean.constant, cov_func=kernel.matern32,
+                params=params, warp_func=WF)
+  path = str(tmp_path / f"{method}.pkl")
+  out = model.train(get_params_path=lambda: path)
+  loaded, (step, loss) = params_utils.load_params(path, include_state=True)
+  assert step == 5 and np.isfinite(loss)
+  assert set(loaded.model) == set(out.model)
+  for k in out.model:
+    assert np.allclose(np.asarray(loaded.model[k], dtype=np.float64),
+                       _np(torch.as_tensor(out.model[k])) if not np.isscalar(out.model[k])
+                       else out.model[k])

@@ -87,3 +87,9 @@ def test_objectives_scenarios(monkeypatch):
   J.test_gp_stats()
   J.test_hgp_stats_average_over_samples()
   J.test_sample_mean_cov_regularizer("squared_exponential")
+
+
+@pytest.mark.parametrize("method", ["adam", "lbfgs"])
+def test_train_checkpoint(monkeypatch, tmp_path, method):  # gp.py:151-157,186-191
+  fake_engine.install(monkeypatch)
+  G.test_train_writes_a_checkpoint(tmp_path, method)

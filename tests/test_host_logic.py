@@ -268,3 +268,36 @@ def test_explicit_matrix_helpers():  # linalg.py:29-33,112-197 (plain torch)
       f_(lambda *a: 0.0)
   with pytest.raises(NotImplementedError):  # not differentiable by the engine
     utils.warp_kind({"lengthscale": utils.squareplus_warp}, "lengthscale")
+
+
+def test_params_checkpoint_round_trip(tmp_path):
+  """params_utils.save_params / load_params / log_params_loss
+  (params_utils.py:64-87,193-207): callables are stored as strings, the cache is
+  not part of a checkpoint, the state tuple (step, loss) comes back."""
+  import numpy as np
+  import torch
+  from hyperbo_b200.basics import definitions as defs
+  from hyperbo_b200.basics import params_utils
+  from hyperbo_b200.gp_utils import objectives, utils
+  params = defs.GPParams(
+      model={"constant": 1.5, "lengthscale": torch.tensor([0.5, 0.7]),
+             "signal_variance": np.float64(1.0), "noise_variance": -3.0},
+      config={"method": "adam", "objective": objectives.nll, "learning_rate": 1e-3},
+      cache={0: defs.GPCache(chol=torch.eye(2), kinvy=torch.ones(2, 1),
+                             needs_update=False)})
+  path = str(tmp_path / "ckpt" / "params.pkl")
+  params_utils.log_params_loss(step=7, params=params, loss=1.25,
+                               warp_func=utils.DEFAULT_WARP_FUNC,
+                               params_save_file=path)
+  loaded, state = params_utils.load_params(path, include_state=True)
+  assert state == (7, 1.25)
+  assert isinstance(loaded, defs.GPParams) and loaded.cache == {}
+  assert loaded.model["constant"] == 1.5
+  assert np.allclose(loaded.model["lengthscale"], [0.5, 0.7])
+  assert isinstance(loaded.config["objective"], str)          # callable -> str
+  as_dict = params_utils.load_params(path, use_gpparams=False)
+  assert set(as_dict) == {"model", "config", "cache", "samples"}
+  with __import__("pytest").raises(FileNotFoundError):
+    params_utils.load_params(str(tmp_path / "missing.pkl"))
+  params_utils.save_to_file(str(tmp_path / "nothing.pkl"), None)  # no state: no file
+  assert not (tmp_path / "nothing.pkl").exists()
