@@ -301,3 +301,22 @@ def test_params_checkpoint_round_trip(tmp_path):
     params_utils.load_params(str(tmp_path / "missing.pkl"))
   params_utils.save_to_file(str(tmp_path / "nothing.pkl"), None)  # no state: no file
   assert not (tmp_path / "nothing.pkl").exists()
+
+
+def test_log_dataset_reports_every_sub_dataset(caplog):
+  """data_utils.log_dataset (data_utils.py:29-69): len, shape, mean / median / min /
+  max per field; empty arrays as nan; non-array fields untouched."""
+  import logging
+  import numpy as np
+  import torch
+  from hyperbo_b200.basics import data_utils
+  from hyperbo_b200.basics import definitions as defs
+  ds = {0: defs.SubDataset(np.arange(6.0).reshape(3, 2), torch.ones(3, 1)),
+        "empty": defs.SubDataset(np.zeros((0, 2)), np.zeros((0, 1)), aligned="a")}
+  with caplog.at_level(logging.INFO):
+    data_utils.log_dataset(ds)
+  text = caplog.text
+  assert "dataset len = 2." in text
+  for word in ("shape", "mean", "median", "min", "max"):
+    assert f"dataset {word}:" in text
+  assert "(3, 2)" in text and "nan" in text and "'a'" in text
