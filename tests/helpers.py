@@ -79,3 +79,20 @@ def load_kat():
     for k in ("nll_task", "grad", "alpha0", "mu", "var", "ei", "pi", "ucb"):
       c[k] = np.asarray(c[k], dtype=np.float64)
   return cases
+
+
+def load_kat_div():
+  """mpmath (60-digit) known answers for the divergence objectives on aligned data
+  (tests/golden/make_mpmath_kat_div.py -- generated WITHOUT importing oracle/)."""
+  import json
+  with open(os.path.join(GOLDEN_DIR, "kat_mpmath_div.json")) as fh:
+    cases = json.load(fh)["cases"]
+  for c in cases:
+    c["dataset"] = {
+        "a%d" % t: (np.asarray(x, dtype=np.float64).reshape(-1, c["d"]),
+                    np.asarray(y, dtype=np.float64), t + 1)
+        for t, (x, y) in enumerate(zip(c["x"], c["y"]))}
+    c["raw"] = np.asarray(c["raw"], dtype=np.float64)
+    for k in ("kl_grad", "euc_grad"):
+      c[k] = np.asarray(c[k], dtype=np.float64)
+  return cases

@@ -209,3 +209,22 @@ def test_training_on_nll_regeuc_decreases_it():
   after = float(objective(mean.constant, kernel.matern52, out, dataset, wf))
   assert len(seen) == 40 and abs(seen[0] - before) < 1e-9 * abs(before)
   assert after < before
+
+
+@pytest.mark.parametrize("case", H.load_kat_div(), ids=lambda c: "katdiv%d_%s_%s" % (
+    c["id"], c["cov"], c["mean"]))
+def test_divergences_match_mpmath_known_answers(case):
+  """hb_nll_grad_mrhs (kl) and hb_euclid_grad (euc), value and gradient, against the
+  60-digit known answers of tests/golden/make_mpmath_kat_div.py (no oracle involved)."""
+  c = case
+  wf = utils.DEFAULT_WARP_FUNC if c["warped"] else None
+  model = H.model_from_raw(c["raw"], c["d"], c["mean"])
+  params = defs.GPParams(model=dict(model))
+  dataset = {k: defs.SubDataset(*v) for k, v in c["dataset"].items()}
+  mf = {"constant": mean.constant, "zero": mean.zero}[c["mean"]]
+  cf = {"squared_exponential": kernel.squared_exponential, "matern32": kernel.matern32,
+        "matern52": kernel.matern52}[c["cov"]]
+  for name, objective in (("kl", objectives.kl), ("euc", objectives.euc)):
+    val, grads = objectives.value_and_grad(objective, mf, cf, params, dataset, wf)
+    assert abs(float(val) - c[name]) < 1e-9 * abs(c[name]), name
+    assert H.rel(H.grad_vec(grads, c["d"]), c[name + "_grad"]) < 1e-7, name

@@ -390,3 +390,20 @@ def test_two_rank_candidate_sharding(monkeypatch):
   same = acfun.shard_candidates(acfun.ei)(model=model, sub_dataset_key=1,
                                           x_queries=xq).numpy()
   assert np.array_equal(same, full)
+
+
+@pytest.mark.parametrize("case", H.load_kat_div(), ids=lambda c: "katdiv%d" % c["id"])
+def test_divergence_programs_match_mpmath_known_answers(monkeypatch, case):
+  """kl (hb_nll_grad_mrhs contract) and euc (hb_euclid_grad contract) programs, value
+  and gradient, against 60-digit answers that were computed without the oracle."""
+  fake_engine.install(monkeypatch)
+  c = case
+  wf = WF if c["warped"] else None
+  model = H.model_from_raw(c["raw"], c["d"], c["mean"])
+  params = defs.GPParams(model=dict(model))
+  dataset = {k: defs.SubDataset(*v) for k, v in c["dataset"].items()}
+  mf, cf = MEANS[c["mean"]], COVS[c["cov"]]
+  for name, objective, tol in (("kl", objectives.kl, 1e-9), ("euc", objectives.euc, 1e-10)):
+    val, grads = objectives.value_and_grad(objective, mf, cf, params, dataset, wf)
+    assert abs(float(val) - c[name]) < 1e-10 * abs(c[name]), name
+    assert H.rel(H.grad_vec(grads, c["d"]), c[name + "_grad"]) < tol, name

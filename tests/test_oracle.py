@@ -359,3 +359,28 @@ def test_oracle_matches_mpmath_known_answers(case):
   _, kinvy, _ = O.solve_gp_linear_system(c["mean"], c["cov"], model, ds[0][0],
                                          ds[0][1], wf)
   assert H.rel(np.ravel(kinvy), c["alpha0"]) < 1e-9
+
+
+# ---- divergence objectives on aligned data against 60-digit known answers -------
+# (tests/golden/make_mpmath_kat_div.py does not import oracle/)
+KAT_DIV = H.load_kat_div()
+
+
+@pytest.mark.parametrize("case", KAT_DIV, ids=lambda c: "katdiv%d_%s_%s_%s" % (
+    c["id"], c["cov"], c["mean"], "warp" if c["warped"] else "raw"))
+def test_oracle_divergences_match_mpmath_known_answers(case):
+  c = case
+  wf = O.DEFAULT_WARP_FUNC if c["warped"] else None
+  model = H.model_from_raw(c["raw"], c["d"], c["mean"])
+  kl = O.multivariate_normal_divergence(c["mean"], c["cov"], model, c["dataset"], wf)
+  assert abs(kl - c["kl"]) <= 1e-11 * abs(c["kl"])
+  euc = O.multivariate_normal_divergence(
+      c["mean"], c["cov"], model, c["dataset"], wf,
+      distance=O.euclidean_multivariate_normal)
+  assert abs(euc - c["euc"]) <= 1e-12 * abs(c["euc"])
+  v, g = O.kl_value_and_grad(c["mean"], c["cov"], model, c["dataset"], wf)
+  gv = H.grad_vec(g, c["d"])
+  if c["mean"] == "zero":
+    gv[0] = 0.0
+  assert abs(v - c["kl"]) <= 1e-11 * abs(c["kl"])
+  assert H.rel(gv, c["kl_grad"]) < 1e-9
