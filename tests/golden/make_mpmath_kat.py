@@ -99,6 +99,15 @@ def predict(cov, mean, warped, raw, x, y, xq, n_tasks):
   alpha = mp.lu_solve(k, r)
   ks = gram(cov, x, xq, ls, sv)                 # (n, nq)
   kinv_ks = mp.inverse(k) * ks
+  # full posterior covariance as GP.predict(full_cov=True, with_noise=True) returns
+  # it (gp.py:295-300, 607-619): noise on the diagonal, then N/(N-1)
+  kss = gram(cov, xq, xq, ls, sv)
+  cov_full = kss - ks.T * kinv_ks
+  for q in range(len(xq)):
+    cov_full[q, q] += nv
+  if n_tasks > 1:
+    cov_full = cov_full * (mp.mpf(n_tasks) / (n_tasks - 1))
+  predict.cov_full = [[cov_full[a, b] for b in range(len(xq))] for a in range(len(xq))]
   mu, var = [], []
   for q in range(len(xq)):
     mu.append(mp.fsum(ks[i, q] * alpha[i] for i in range(n)) + const)
@@ -175,6 +184,7 @@ def build_case(cid, cov, mean, warped, ns, d, rng, dup=False):
       "x": [x.tolist() for x, _ in tasks_np], "y": [yv.tolist() for _, yv in tasks_np],
       "nll_task": fl(per_task), "mean_nll": f(val), "grad": fl(grad),
       "xq": xq_np.tolist(), "alpha0": fl(alpha), "mu": fl(mu), "var": fl(var),
+      "cov_full": [fl(row) for row in predict.cov_full],
       "ei": fl(ei), "pi": fl(pi), "ucb": fl(ucb),
   }
 

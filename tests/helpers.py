@@ -76,7 +76,8 @@ def load_kat():
                     for t, (x, y) in enumerate(zip(c["x"], c["y"]))}
     c["raw"] = np.asarray(c["raw"], dtype=np.float64)
     c["xq"] = np.asarray(c["xq"], dtype=np.float64).reshape(-1, c["d"])
-    for k in ("nll_task", "grad", "alpha0", "mu", "var", "ei", "pi", "ucb"):
+    for k in ("nll_task", "grad", "alpha0", "mu", "var", "ei", "pi", "ucb",
+              "cov_full"):
       c[k] = np.asarray(c[k], dtype=np.float64)
   return cases
 

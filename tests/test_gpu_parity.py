@@ -331,3 +331,9 @@ def test_cuda_matches_mpmath_known_answers(eng, case):
     assert H.rel(mu.cpu().numpy().ravel(), c["mu"]) < TOL_PRED
     assert H.rel(var.cpu().numpy().ravel(), c["var"]) < TOL_PRED
     assert H.rel(acq.cpu().numpy().ravel(), c[key]) < TOL_PRED
+  # full posterior covariance (hb_predict_cov) against the same known answers
+  mu, cov = eng.predict_cov(kid, mid, eng.tensor(x0), cache, c["raw"], mask, c["xq"],
+                            noise_flag=1.0, var_scale=scale)
+  assert H.rel(mu.cpu().numpy().ravel(), c["mu"]) < TOL_PRED
+  assert np.abs(cov.cpu().numpy() - c["cov_full"]).max() < \
+      TOL_PRED * np.abs(c["cov_full"]).max()

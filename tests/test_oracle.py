@@ -356,6 +356,9 @@ def test_oracle_matches_mpmath_known_answers(case):
   for name in ("ei", "pi", "ucb"):
     a = O.acquisition(name, c["mean"], c["cov"], model, ds, 0, c["xq"], wf)
     assert H.rel(np.ravel(a), c[name]) < 1e-8, name
+  _, cov_full = O.gp_predict(c["mean"], c["cov"], model, ds, c["xq"], 0, wf,
+                             full_cov=True)
+  assert np.abs(cov_full - c["cov_full"]).max() < 1e-9 * np.abs(c["cov_full"]).max()
   _, kinvy, _ = O.solve_gp_linear_system(c["mean"], c["cov"], model, ds[0][0],
                                          ds[0][1], wf)
   assert H.rel(np.ravel(kinvy), c["alpha0"]) < 1e-9
