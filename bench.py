@@ -400,6 +400,48 @@ def run_ours(args):
                           "task's 512 points on the device (hb_subsample in the "
                           "step's CUDA graph), then NLL+grad+Adam on 256 x 256 x 8"}
 
+  # ---- the reference's second objective (8f rank 3): empirical KL on aligned data,
+  # value + gradient per call: one factorisation per sub-dataset (hb_nll_grad_mrhs)
+  # against the m + 2 weighted-task form.  Extra evidence only: never fails the line.
+  kl_objective = None
+  if world == 1 and not args.no_train_e2e and not f32:
+    try:
+      from hyperbo_b200.basics import definitions as defs, params_utils
+      from hyperbo_b200.gp_utils import kernel, mean, objectives, utils
+      rng = np.random.default_rng(5)
+      nk, mk = 512, 20
+      xk = rng.uniform(size=(nk, d))
+      yk = np.sin(xk.sum(1))[:, None] + 0.3 * rng.standard_normal((nk, mk))
+      dsk = {"a": defs.SubDataset(xk, yk, aligned=1)}
+      rawk, maskk, _ = params_utils.pack_raw(
+          {"constant": 0.1, "signal_variance": 0.0, "noise_variance": -3.0,
+           "lengthscale": np.zeros(d)}, d, True, utils.DEFAULT_WARP_FUNC)
+      rawk = eng.tensor(rawk)
+      kl_objective = {"n": nk, "m": mk, "d": d, "unit": "ms per value+gradient"}
+      vals = {}
+      for flag, key in ((True, "multi_rhs_ms"), (False, "weighted_tasks_ms")):
+        objectives.KL_MULTI_RHS = flag
+        prog = objectives.compile_objective(objectives.kl, mean.constant,
+                                            kernel.matern52, dsk)
+        for _ in range(3):
+          sk = prog.sums(rawk, maskk)
+        torch.cuda.synchronize(dev)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(20):
+          sk = prog.sums(rawk, maskk)
+        k1.record()
+        torch.cuda.synchronize(dev)
+        kl_objective[key] = k0.elapsed_time(k1) / 20
+        vals[key] = float(sk[0])
+      objectives.KL_MULTI_RHS = True
+      kl_objective["speedup"] = (kl_objective["weighted_tasks_ms"] /
+                                 kl_objective["multi_rhs_ms"])
+      kl_objective["value_rel_diff"] = abs(
+          vals["multi_rhs_ms"] - vals["weighted_tasks_ms"]) / abs(vals["weighted_tasks_ms"])
+    except Exception as e:  # pylint: disable=broad-except
+      kl_objective = {"error": repr(e)}
+
   # ---- factorise-only timings: the second half of BASELINE's metric
   def chol_block(tag, T_, n_, d_, kid, reps):
     rng = np.random.default_rng(11)
@@ -569,6 +611,7 @@ def run_ours(args):
            "k_lauum_grad": ms_fused,
            "reduce": 2 * prof_ms[3] / max(prof_cnt[3], 1)}),
       "subsampled_training": subsampled,
+      "kl_objective": kl_objective,
       "other_precision": other,
       "cpu_baseline": cpu,
   }
