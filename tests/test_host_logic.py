@@ -320,3 +320,51 @@ def test_log_dataset_reports_every_sub_dataset(caplog):
   for word in ("shape", "mean", "median", "min", "max"):
     assert f"dataset {word}:" in text
   assert "(3, 2)" in text and "nan" in text and "'a'" in text
+
+
+def test_round_robin_sharding_is_a_balanced_partition():
+  """objectives._shard with a rotating start (several short launches must not all
+  land on rank 0): for every (items, world, start) the ranks' shares are disjoint,
+  cover everything and differ by at most one."""
+  from hypothesis import given, settings, strategies as st
+  from hyperbo_b200.gp_utils import objectives
+
+  @settings(max_examples=200, deadline=None)
+  @given(st.integers(0, 40), st.integers(1, 9), st.integers(0, 100))
+  def check(n, world, start):
+    items = list(range(n))
+    shares = [objectives._shard(items, r, world, start) for r in range(world)]
+    flat = sorted(x for s in shares for x in s)
+    assert flat == items
+    sizes = [len(s) for s in shares]
+    assert max(sizes) - min(sizes) <= 1
+    # continuing the rotation after this launch keeps the TOTAL balanced too
+    nxt = [objectives._shard(items, r, world, start + n) for r in range(world)]
+    tot = [len(a) + len(b) for a, b in zip(shares, nxt)]
+    assert max(tot) - min(tot) <= 1
+
+  check()
+
+
+def test_lbfgs_evaluator_memo_is_bounded_and_exact():
+  """basics/lbfgs._Evaluator: hits return the stored pair, the memo never exceeds
+  `keep` entries, prefetch is a no-op without a multi-point objective."""
+  import numpy as np
+  from hyperbo_b200.basics import lbfgs
+  n = {"c": 0}
+
+  def fn(x):
+    n["c"] += 1
+    return float(x @ x), 2 * x
+
+  ev = lbfgs._Evaluator(fn, keep=3)
+  pts = [np.array([float(i), 1.0]) for i in range(5)]
+  for p in pts:
+    ev(p)
+  assert n["c"] == 5 and len(ev.memo) == 3
+  v, g = ev(pts[-1])                      # hit
+  assert n["c"] == 5 and v == float(pts[-1] @ pts[-1])
+  ev(pts[0])                              # evicted earlier: evaluated again
+  assert n["c"] == 6
+  ev.prefetch([np.array([9.0, 9.0]), np.array([8.0, 8.0])])
+  assert n["c"] == 6 and ev.calls == 6 and ev.points == 6
